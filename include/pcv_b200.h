@@ -1,0 +1,230 @@
+/*
+ * pcv_b200.h — C ABI of libpcv_b200.so, the sm_100a slate-generation hot path.
+ *
+ * The reference (CharlieMat/PivotCVAE) has no FFI: its boundary is the Python
+ * class API (models/cvae.py, models/pivotcvae.py, models/listcvae.py,
+ * env/response_model.py, train_generative.py).  This header is the layer a
+ * maintainer would bind *underneath* those classes (ctypes stub in
+ * INTEGRATION.md).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch), except
+ *    descriptor structs (host) and out-params named *_host;
+ *  - every op takes a cudaStream_t (as void*) and is asynchronous on it;
+ *  - return 0 on success, <0 on error (pcv_last_error() gives the text);
+ *  - no allocation inside ops: scratch comes from the caller through the
+ *    *_workspace_bytes() queries;
+ *  - float = IEEE binary32, indices = int64 (torch.long), row-major tensors.
+ *  - there is no CPU fallback: a non-sm_100 device yields PCV_ERR_ARCH.
+ */
+#ifndef PCV_B200_H
+#define PCV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCV_ABI_VERSION 1
+
+#define PCV_OK 0
+#define PCV_ERR_ARG (-1)
+#define PCV_ERR_ARCH (-2)
+#define PCV_ERR_CUDA (-3)
+#define PCV_ERR_WORKSPACE (-4)
+#define PCV_ERR_UNSUPPORTED (-5)
+
+typedef void *pcv_stream_t; /* cudaStream_t */
+
+int pcv_abi_version(void);
+const char *pcv_last_error(void);
+/* 0 when `device` is compute capability 10.x (B200), PCV_ERR_ARCH otherwise. */
+int pcv_device_ok(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t pcv_launch_count(void);
+
+/* ------------------------------------------------------------------ */
+/* Item table (the frozen, row-L2-normalised catalog; cvae.py:27-33)   */
+/* ------------------------------------------------------------------ */
+typedef struct pcv_table pcv_table;
+
+/* W: [n_rows, dim] fp32 row-major, 16-byte aligned.  row_offset is the global
+ * index of row 0 (vocab-parallel shards); indices returned by
+ * pcv_score_select are global (= local + row_offset).  The table is borrowed,
+ * not copied: it must outlive the handle.  dim must be a multiple of 4, <= 128. */
+int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset,
+                     pcv_table **out);
+void pcv_table_destroy(pcv_table *t);
+/* F.normalize(W, p=2, dim=1, eps=1e-12) row-wise, out-of-place (cvae.py:31,39). */
+int pcv_normalize_rows(const float *W, int64_t n_rows, int dim, float *out,
+                       pcv_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused score + select over the catalog                               */
+/*   greedy : cvae.py:97-101 (get_recommended_item), pivotcvae.py:191  */
+/*   exprace: pivotcvae.py:349-351,389-391 (Categorical(sigmoid(.)))   */
+/* ------------------------------------------------------------------ */
+#define PCV_SELECT_GREEDY 0  /* argmax_j <q, w_j>, ties -> lowest j               */
+#define PCV_SELECT_EXPRACE 1 /* argmax_j sigmoid(<q, w_j>) / E_j, E_j ~ Exp(1)     */
+
+#define PCV_ENGINE_AUTO 0
+#define PCV_ENGINE_SIMT 1    /* exact fp32 FMA chain on CUDA cores                  */
+#define PCV_ENGINE_TCGEN05 2 /* tf32 tcgen05 filter + exact fp32 refine (greedy)    */
+
+typedef struct {
+  int mode;           /* PCV_SELECT_*                                              */
+  int engine;         /* PCV_ENGINE_*                                              */
+  const float *noise; /* exprace: [M, n_rows] Exp(1) draws (parity mode) or NULL   */
+  uint64_t seed;      /* exprace with noise==NULL: Philox4x32-10 key               */
+  uint64_t offset;    /* Philox stream offset (added to the row counter word)      */
+  int no_repeat;      /* reserved: must be 0 (the reference has no mask) */
+} pcv_select_opts;
+
+int pcv_score_select_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
+/* Q: [M, dim].  out_idx: [M] int64 (global index).  out_val: [M] fp32 (the
+ * winning score; for exprace the winning key) or NULL. */
+int pcv_score_select(const pcv_table *t, const float *Q, int64_t M,
+                     const pcv_select_opts *opts, int64_t *out_idx, float *out_val,
+                     void *workspace, size_t workspace_bytes, pcv_stream_t stream);
+/* API-parity path for forward()'s `p` (pivotcvae.py:274, listcvae.py:166):
+ * out[M, n_rows] = Q @ W^T, exact fp32 sequential-k FMA chain. */
+int pcv_score_logits(const pcv_table *t, const float *Q, int64_t M, float *out,
+                     pcv_stream_t stream);
+/* Materialise the Exp(1) draws the fused exprace kernel uses for (seed, offset):
+ * out[M, n_rows]; test hook for the Philox path. */
+int pcv_philox_exponential(uint64_t seed, uint64_t offset, int64_t M, int64_t n_cols,
+                           int64_t col_offset, float *out, pcv_stream_t stream);
+/* Vocab-parallel merge: vals/idx are [G, M] partials gathered from G
+ * shards in shard order; winner = max val, ties -> lowest global index. */
+int pcv_vp_merge_select(const float *vals, const int64_t *idx, int G, int64_t M,
+                        int64_t *out_idx, float *out_val, pcv_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused MLP blocks (encoder / prior / PSM / SCM / ListCVAE decoder /  */
+/* response MLP): concat+gather+one-hot prologue, Linear+activation    */
+/* chain with weights streamed through shared memory, optional         */
+/* reparameterisation epilogue.                                        */
+/*   pivotcvae.py:159-174,197-240,278-291  listcvae.py:90-132          */
+/*   cvae.py:79-92   env/response_model.py:76-87                       */
+/* ------------------------------------------------------------------ */
+#define PCV_ACT_NONE 0
+#define PCV_ACT_LEAKY 1 /* nn.LeakyReLU(0.01) (cvae.py:43)          */
+#define PCV_ACT_RELU 2  /* F.relu (env/response_model.py:85)        */
+
+typedef struct {
+  const float *W; /* [n_out, n_in] row-major == nn.Linear.weight */
+  const float *b; /* [n_out]                                     */
+  int n_in, n_out, act;
+} pcv_linear;
+
+#define PCV_SEG_DENSE 0  /* ptr: float[B, width]                                      */
+#define PCV_SEG_ONEHOT 1 /* ptr: float r[B, count]; one-hot(sum_l r) of width count+1 */
+#define PCV_SEG_GATHER 2 /* ptr: float table[*, width]; idx: int64[B, count] -> count*width floats */
+
+#define PCV_NORM_NONE 0
+#define PCV_NORM_SEGMENT 1 /* L2-normalise the whole segment (response_model.py:78)  */
+
+typedef struct {
+  int kind;
+  const void *ptr;
+  const int64_t *idx;
+  int width; /* row width (DENSE: segment width; GATHER: table dim)  */
+  int count; /* ONEHOT: slate size; GATHER: rows gathered per sample */
+  int norm;  /* PCV_NORM_*                                           */
+} pcv_segment;
+
+#define PCV_MAX_SEGMENTS 6
+#define PCV_MAX_LAYERS 8
+#define PCV_MAX_WIDTH 512 /* widest layer / input supported */
+
+typedef struct {
+  int n_segments;
+  pcv_segment seg[PCV_MAX_SEGMENTS];
+  int n_layers;
+  pcv_linear layer[PCV_MAX_LAYERS];
+  /* output: out[b*out_ld + out_col0 + j] = last layer j */
+  float *out;
+  int out_ld, out_col0;
+  /* optional: also copy input segment `copy_seg` (>=0) to out[b*out_ld + 0 ..] —
+   * used to place the pivot row at slot 0 of rx (pivotcvae.py:224). */
+  int copy_seg;
+  /* optional saved tensors for backward (NULL to skip): x0[B, n_in0] is the
+   * assembled input, acts[l] is [B, n_out_l] post-activation output of layer l
+   * (l < n_layers-1; the last layer's output is `out`). */
+  float *x0;
+  float *acts[PCV_MAX_LAYERS];
+  /* optional reparameterisation epilogue (cvae.py:79-83): the last layer emits
+   * [mu | logvar] (2*latent); z[b, j] = eps*exp(0.5*logvar)+mu.  eps from
+   * `eps` ([B, latent], parity mode) or Philox(seed, offset) normals. */
+  int latent; /* 0 = no reparam */
+  const float *eps;
+  uint64_t seed, offset;
+  float *z;       /* [B, latent] */
+  float *eps_out; /* optional [B, latent]: the eps actually used (for backward) */
+} pcv_mlp_desc;
+
+int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream);
+
+/* KL(q || p) between diagonal Gaussians, summed over batch and latent
+ * (train_generative.py:61) plus analytic grads (any grad pointer may be NULL).
+ * kl_out: device scalar (overwritten, not accumulated). */
+int pcv_kl_fwd_bwd(const float *mu, const float *logvar, const float *pmu,
+                   const float *plogvar, int64_t n, float *kl_out, float *dmu,
+                   float *dlogvar, float *dpmu, float *dplogvar, pcv_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused streaming masked soft-max cross-entropy over the catalog      */
+/*   train_generative.py:36-42 (downsample), :59 (CrossEntropyLoss),   */
+/*   pivotcvae.py:274 (logits) — logits never reach HBM.               */
+/* loss_row[i] = log(sum_{j in mask_i} e^{x_ij} + (N-|mask_i|)) - x_{i,t_i}   */
+/* mask_i = {t_i} U Bernoulli(keep_prob) per (i, j); masked-out logits are 0 */
+/* (not -inf) exactly as `pred * mask` does.               */
+/* dq[i,:] = d loss_row[i] / d q_i  (the table is frozen: no dW).      */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  double keep_prob;        /* n_neg / N; >= 1 means full-catalog soft-max, no RNG    */
+  const uint32_t *bitmask; /* parity mode: [M, ceil(N/32)] bit j%32 of word j/32 = Bernoulli draw (target is OR-ed in by the kernel) */
+  uint64_t seed, offset;   /* Philox mode (bitmask == NULL && keep_prob < 1)         */
+} pcv_ce_mask;
+
+int pcv_ce_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
+/* Single streaming pass producing loss rows, log-sum-exp and dq (forward and
+ * the gradient in one pass; backward is a scale by the upstream gradient).
+ * For vocab-parallel shards targets outside [row_offset, row_offset+n_rows) are
+ * skipped and partial (max, sumexp, target_logit, dq_unnormalised) are returned
+ * through pcv_ce_partial instead. */
+int pcv_ce_fwd_bwd(const pcv_table *t, const float *Q, const int64_t *targets,
+                   int64_t M, const pcv_ce_mask *mask, float *loss_rows, float *lse,
+                   float *dq, void *workspace, size_t workspace_bytes,
+                   pcv_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Simulator response models, gather-plus-dot (env/response_model.py)  */
+/*   URM      :129-150   URM_P :286-295   URM_P_MR :315-323            */
+/* ------------------------------------------------------------------ */
+#define PCV_URM 0
+#define PCV_URM_P 1
+#define PCV_URM_P_MR 2
+
+typedef struct {
+  int variant;
+  const float *doc_table;  /* [I, D] raw (un-normalised) item embeddings      */
+  const float *user_table; /* [U, D] raw user embeddings (used un-normalised, response_model.py:145) */
+  const float *item_bias;  /* [I]                                             */
+  const float *user_bias;  /* [U]                                             */
+  const float *pos_bias;   /* [L]       (URM_P*)                              */
+  const float *pos_dep;    /* [L*D] flat, read as a (D, L) view (response_model.py:292) */
+  float mr_factor;         /* URM_P_MR                                        */
+  int L, D;
+} pcv_urm_desc;
+
+/* out: [B, L] final score (URM: sigmoid(raw); URM_P: sigmoid(raw)+pos terms; ...). */
+int pcv_urm_fwd(const pcv_urm_desc *d, const int64_t *slates, const int64_t *users,
+                int64_t B, float *out, pcv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCV_B200_H */

@@ -1,0 +1,368 @@
+// ce.cu — fused streaming masked soft-max cross-entropy over the catalog:
+// loss rows, log-sum-exp AND d(loss_row)/dq in one pass; the (M x N) logits,
+// the Bernoulli mask and the soft-max never reach HBM.
+//
+// Replaces (reference file:line)
+//   pivotcvae.py:274 / listcvae.py:166   p = mm(prox_emb, table.t())        (M x N, materialised)
+//   train_generative.py:36-42            downsample: mask = onehot(target) U Bernoulli(n_neg/N); pred*mask
+//   train_generative.py:59               CrossEntropyLoss (log-softmax + nll), and their backward
+//
+// Semantics kept: masked-OUT logits become 0 (not -inf):
+//   lse_i  = log( sum_{j in mask_i} e^{x_ij} + (N - |mask_i|) )
+//   loss_i = lse_i - x_{i,t_i}
+//   dq_i   = sum_{j in mask_i} softmax_ij * w_j - w_{t_i}          (table frozen: no dW)
+//
+// Layout mirrors score_select.cu: CTA = 8 warps x R rows, catalog split over
+// blockIdx.y, cp.async double-buffered float4-SoA tiles.  Each lane keeps an
+// online-softmax state (running max m, sum l, dq accumulator) for its rows;
+// lanes, then splits, are merged with the usual rescale.
+#include "pcv_common.cuh"
+
+namespace pcv {
+
+constexpr int CE_WARPS = 8;
+constexpr int CE_THREADS = CE_WARPS * 32;
+constexpr int CE_TILE_FLOATS = 8192;
+
+enum { CE_DENSE = 0, CE_BITMASK = 1, CE_PHILOX = 2 };
+
+template <int D>
+struct CECfg {
+  static constexpr int R = (D <= 8) ? 4 : (D <= 16 ? 2 : 1);
+  static constexpr int ROWS = CE_WARPS * R;
+  static constexpr int TILE = (CE_TILE_FLOATS / D) < 128 ? 128 : (CE_TILE_FLOATS / D);
+  static constexpr int C4 = D / 4;
+  static constexpr size_t SMEM = 2ull * TILE * D * sizeof(float);
+};
+
+struct CEPlan {
+  int rows_per_cta, tile, row_tiles, n_split;
+  int64_t items_per_split;
+  int rec;  // floats per (split,row) partial record: m, l, cnt, dq[D]
+  size_t ws_bytes;
+};
+
+static int ce_rows_for(int D) {
+  switch (D) {
+    case 4: return CECfg<4>::ROWS;
+    case 8: return CECfg<8>::ROWS;
+    case 16: return CECfg<16>::ROWS;
+    case 32: return CECfg<32>::ROWS;
+    case 64: return CECfg<64>::ROWS;
+  }
+  return 0;
+}
+
+static int ce_plan(const Table *t, int64_t M, CEPlan *p) {
+  p->rows_per_cta = ce_rows_for(t->dim);
+  if (!p->rows_per_cta) return PCV_ERR_UNSUPPORTED;
+  p->tile = CE_TILE_FLOATS / t->dim < 128 ? 128 : CE_TILE_FLOATS / t->dim;
+  p->row_tiles = (int)((M + p->rows_per_cta - 1) / p->rows_per_cta);
+  int64_t n_tiles = (t->n_rows + p->tile - 1) / p->tile;
+  int64_t want = (4LL * t->sm_count + p->row_tiles - 1) / p->row_tiles;
+  int64_t max_split = (n_tiles + 3) / 4;
+  if (max_split < 1) max_split = 1;
+  int64_t ns = want < 1 ? 1 : (want > max_split ? max_split : want);
+  int64_t tps = (n_tiles + ns - 1) / ns;
+  ns = (n_tiles + tps - 1) / tps;
+  p->n_split = (int)ns;
+  p->items_per_split = tps * p->tile;
+  p->rec = 3 + t->dim;
+  p->ws_bytes = (size_t)ns * (size_t)M * p->rec * sizeof(float);
+  return PCV_OK;
+}
+
+__device__ __forceinline__ void ce_cp_async16(void *smem, const void *gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+
+// Bernoulli(keep) draw for (row, global column j): 32-bit Philox word < thresh.
+// Same 128-column block mapping as the exponential race (4 columns per call).
+__device__ __forceinline__ bool bern_philox(uint64_t seed, uint64_t offset, int64_t row,
+                                            int64_t jglobal, uint32_t thresh) {
+  int64_t call = ((jglobal >> 7) << 5) + (jglobal & 31);
+  int e = (int)((jglobal >> 5) & 3);
+  uint64_t r = (uint64_t)row + offset;
+  Philox4 p = philox4x32_10((uint32_t)call, (uint32_t)r, (uint32_t)(r >> 32), PCV_STREAM_BERNOULLI,
+                            (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t w = e == 0 ? p.x : (e == 1 ? p.y : (e == 2 ? p.z : p.w));
+  return w < thresh;
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(CE_THREADS, 2)
+ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
+          const float *__restrict__ Q, const int64_t *__restrict__ targets, int64_t M,
+          int64_t items_per_split, const uint32_t *__restrict__ bitmask, int64_t mask_words,
+          uint64_t seed, uint64_t offset, uint32_t thresh, float *__restrict__ part) {
+  using Cfg = CECfg<D>;
+  constexpr int R = Cfg::R, TILE = Cfg::TILE, C4 = Cfg::C4, REC = 3 + D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *tile4 = reinterpret_cast<float4 *>(smem_raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * Cfg::ROWS + (int64_t)warp * R;
+  const int64_t j_begin = (int64_t)blockIdx.y * items_per_split;
+  const int64_t j_end = min(n_rows, j_begin + items_per_split);
+  const int n_tiles = (int)((j_end - j_begin + TILE - 1) / TILE);
+
+  float q[R][D];
+  int64_t tgt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool ok = (row0 + r) < M;
+    tgt[r] = ok ? targets[row0 + r] - row_offset : -1;
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(Q + (row0 + r) * D) + c)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      q[r][4 * c + 0] = v.x; q[r][4 * c + 1] = v.y; q[r][4 * c + 2] = v.z; q[r][4 * c + 3] = v.w;
+    }
+  }
+  float m[R], l[R], acc[R][D];
+  int cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f; cnt[r] = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[r][k] = 0.f;
+  }
+
+  auto load_tile = [&](int t, int buf) {
+    const int64_t base = j_begin + (int64_t)t * TILE;
+    float4 *dst = tile4 + (size_t)buf * C4 * TILE;
+    const float4 *src = reinterpret_cast<const float4 *>(W + base * D);
+#pragma unroll 4
+    for (int f = threadIdx.x; f < TILE * C4; f += CE_THREADS) {
+      int item = f / C4, c = f % C4;
+      bool valid = (base + item) < j_end;
+      ce_cp_async16(dst + c * TILE + item, valid ? (const void *)(src + f) : (const void *)W, valid);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  if (n_tiles > 0) load_tile(0, 0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) {
+      load_tile(t + 1, (t + 1) & 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    const float4 *cur = tile4 + (size_t)(t & 1) * C4 * TILE;
+    const int64_t base = j_begin + (int64_t)t * TILE;
+    const int n_valid = (int)min((int64_t)TILE, j_end - base);
+    for (int i = lane; i < n_valid; i += 32) {
+      const int64_t j = base + i;
+      bool in[R];
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        bool b;
+        if (MODE == CE_DENSE) {
+          b = true;
+        } else if (MODE == CE_BITMASK) {
+          // base and i-lane are multiples of 32: the warp shares one word per row
+          uint32_t word = (row0 + r < M) ? __ldg(bitmask + (row0 + r) * mask_words + (j >> 5)) : 0u;
+          b = (word >> (j & 31)) & 1u;
+        } else {
+          b = bern_philox(seed, offset, row0 + r, j + row_offset, thresh);
+        }
+        b = b || (j == tgt[r]);
+        in[r] = b;
+        any = any || b;
+      }
+      if (!any) continue;
+      float w[D];
+#pragma unroll
+      for (int c = 0; c < C4; ++c) {
+        const float4 v = cur[c * TILE + i];
+        w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!in[r]) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fmaf(q[r][k], w[k], s);
+        cnt[r] += 1;
+        if (s > m[r]) {
+          const float sc = __expf(m[r] - s);  // m=-inf -> 0
+          l[r] *= sc;
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc[r][k] *= sc;
+          m[r] = s;
+        }
+        const float p = __expf(s - m[r]);
+        l[r] += p;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc[r][k] = fmaf(p, w[k], acc[r][k]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // merge lanes (rescale to the common max)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float mw = warp_max(m[r]);
+    const float sc = (m[r] == -INFINITY) ? 0.f : __expf(m[r] - mw);
+    float lw = warp_sum(l[r] * sc);
+    int cw = cnt[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
+    float a[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) a[k] = warp_sum(acc[r][k] * sc);
+    if (lane == 0 && row0 + r < M) {
+      float *rec = part + ((int64_t)blockIdx.y * M + row0 + r) * REC;
+      rec[0] = mw; rec[1] = lw; rec[2] = __int_as_float(cw);
+#pragma unroll
+      for (int k = 0; k < D; ++k) rec[3 + k] = a[k];
+    }
+  }
+}
+
+// One thread per row: merge split partials, add the masked-out mass, emit
+// loss / lse / dq.  Target logit re-derived with the exact FMA chain.
+__global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, int64_t M, int D,
+                                   const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
+                                   const float *__restrict__ Q, const int64_t *__restrict__ targets,
+                                   float *__restrict__ loss_rows, float *__restrict__ lse_out,
+                                   float *__restrict__ dq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int REC = 3 + D;
+  float mx = -INFINITY;
+  int64_t cnt = 0;
+  for (int s = 0; s < n_split; ++s) {
+    const float *rec = part + ((int64_t)s * M + i) * REC;
+    mx = fmaxf(mx, rec[0]);
+    cnt += __float_as_int(rec[2]);
+  }
+  const int64_t n_out = n_rows - cnt;  // masked-out logits are exactly 0
+  if (n_out > 0) mx = fmaxf(mx, 0.f);
+  float L = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float *rec = part + ((int64_t)s * M + i) * REC;
+    if (rec[0] != -INFINITY) L += rec[1] * __expf(rec[0] - mx);
+  }
+  L += (float)n_out * __expf(-mx);
+  const float lse = mx + logf(L);
+  const int64_t t = targets[i] - row_offset;
+  const float *wt = W + t * D;
+  const float *qi = Q + i * D;
+  float xt = 0.f;
+  for (int k = 0; k < D; ++k) xt = fmaf(qi[k], wt[k], xt);
+  if (loss_rows) loss_rows[i] = lse - xt;
+  if (lse_out) lse_out[i] = lse;
+  if (dq) {
+    const float inv = 1.f / L;
+    for (int k = 0; k < D; ++k) {
+      float a = 0.f;
+      for (int s = 0; s < n_split; ++s) {
+        const float *rec = part + ((int64_t)s * M + i) * REC;
+        if (rec[0] != -INFINITY) a += rec[3 + k] * __expf(rec[0] - mx);
+      }
+      dq[i * D + k] = a * inv - wt[k];
+    }
+  }
+}
+
+template <int D, int MODE>
+static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
+                     int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
+                     uint64_t offset, uint32_t thresh, float *part, cudaStream_t st) {
+  using Cfg = CECfg<D>;
+  auto kern = ce_kernel<D, MODE>;
+  static bool attr_set[64] = {false};
+  if (!attr_set[t->device & 63]) {
+    PCV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set[t->device & 63] = true;
+  }
+  dim3 grid((unsigned)p.row_tiles, (unsigned)p.n_split);
+  kern<<<grid, CE_THREADS, Cfg::SMEM, st>>>(t->W, t->n_rows, t->row_offset, Q, targets, M,
+                                            p.items_per_split, bitmask, mask_words, seed, offset,
+                                            thresh, part);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+template <int MODE>
+static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
+                       int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
+                       uint64_t offset, uint32_t thresh, float *part, cudaStream_t st) {
+  switch (t->dim) {
+    case 4: return launch_ce<4, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+    case 8: return launch_ce<8, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+    case 16: return launch_ce<16, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+    case 32: return launch_ce<32, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+    case 64: return launch_ce<64, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+  }
+  set_error("ce: dim %d unsupported (use 4, 8, 16, 32 or 64)", t->dim);
+  return PCV_ERR_UNSUPPORTED;
+}
+
+}  // namespace pcv
+
+using namespace pcv;
+
+extern "C" {
+
+int pcv_ce_workspace_bytes(const pcv_table *th, int64_t M, size_t *bytes_host) {
+  PCV_CHECK_ARG(th && bytes_host, "NULL pointer");
+  PCV_CHECK_ARG(M > 0, "M must be > 0");
+  const Table *t = reinterpret_cast<const Table *>(th);
+  CEPlan p;
+  if (ce_plan(t, M, &p) != PCV_OK) {
+    set_error("ce: dim %d unsupported", t->dim);
+    return PCV_ERR_UNSUPPORTED;
+  }
+  *bytes_host = (p.ws_bytes + 255) & ~(size_t)255;
+  return PCV_OK;
+}
+
+int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, int64_t M,
+                   const pcv_ce_mask *mask, float *loss_rows, float *lse, float *dq,
+                   void *workspace, size_t workspace_bytes, pcv_stream_t stream) {
+  PCV_CHECK_ARG(th && Q && targets && mask, "NULL pointer");
+  PCV_CHECK_ARG(M > 0, "M must be > 0");
+  const Table *t = reinterpret_cast<const Table *>(th);
+  PCV_CHECK_ARG(t->n_rows < 0x7fffffffLL, "shard larger than 2^31-1 rows");
+  PCV_CHECK_ARG(t->row_offset == 0, "vocab-parallel CE partials are not exposed yet: row_offset must be 0");
+  PCV_CHECK_ARG(mask->keep_prob > 0.0, "keep_prob must be > 0");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  CEPlan p;
+  if (ce_plan(t, M, &p) != PCV_OK) {
+    set_error("ce: dim %d unsupported", t->dim);
+    return PCV_ERR_UNSUPPORTED;
+  }
+  if (!workspace || workspace_bytes < p.ws_bytes) {
+    set_error("ce: workspace too small (%zu < %zu)", workspace_bytes, p.ws_bytes);
+    return PCV_ERR_WORKSPACE;
+  }
+  float *part = reinterpret_cast<float *>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t mask_words = (t->n_rows + 31) / 32;
+  if (mask->bitmask) {
+    rc = ce_dispatch<CE_BITMASK>(t, p, Q, targets, M, mask->bitmask, mask_words, 0, 0, 0, part, st);
+  } else if (mask->keep_prob >= 1.0) {
+    rc = ce_dispatch<CE_DENSE>(t, p, Q, targets, M, nullptr, 0, 0, 0, 0, part, st);
+  } else {
+    double th32 = mask->keep_prob * 4294967296.0;
+    uint32_t thresh = th32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)th32;
+    rc = ce_dispatch<CE_PHILOX>(t, p, Q, targets, M, nullptr, 0, mask->seed, mask->offset, thresh,
+                                part, st);
+  }
+  if (rc != PCV_OK) return rc;
+  ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(
+      part, p.n_split, M, t->dim, t->W, t->n_rows, t->row_offset, Q, targets, loss_rows, lse, dq);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+}  // extern "C"
