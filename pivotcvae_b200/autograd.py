@@ -1,0 +1,164 @@
+"""autograd glue around the fused CUDA blocks.
+
+Forward passes are single calls into libpcv_b200.so.  Backward of the catalog
+cross-entropy is free (the forward kernel already produced d loss/d q); backward
+of the small MLP blocks is a handful of plain GEMMs over saved activations,
+issued through torch.mm (cuBLAS) — plain library GEMMs, not part of the fused
+hot path.  The PSM block never needs a backward.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+class MlpSpec:
+    """Static description of one fused block.
+
+    segs: list of ('dense', k) | ('onehot', r) | ('gather', table, idx[, normalize]);
+          ('dense', k) refers to the k-th differentiable dense input of the call.
+    acts: activation id per layer.
+    """
+
+    def __init__(self, segs, acts, latent=0, eps=None, seed=0, offset=0, out_ld=None, out_col0=0, copy_seg=-1,
+                 save=True):
+        self.segs, self.acts = segs, list(acts)
+        self.save = save
+        self.latent, self.eps, self.seed, self.offset = latent, eps, seed, offset
+        self.out_ld, self.out_col0, self.copy_seg = out_ld, out_col0, copy_seg
+
+    def build_segments(self, dense):
+        out = []
+        for s in self.segs:
+            if s[0] == "dense":
+                out.append(ops.Dense(dense[s[1]]))
+            elif s[0] == "onehot":
+                out.append(ops.OneHot(s[1]))
+            else:
+                out.append(ops.Gather(s[1], s[2], normalize=(len(s) > 3 and s[3])))
+        return out
+
+
+def _act_grad(g, a_out, act):
+    if act == L.ACT_LEAKY:
+        return g * torch.where(a_out > 0, 1.0, 0.01)
+    if act == L.ACT_RELU:
+        return g * (a_out > 0).to(g.dtype)
+    return g
+
+
+class FusedMLPFn(torch.autograd.Function):
+    """apply(spec, B, n_dense, *dense_inputs, W0, b0, W1, b1, ...) -> out[, z]"""
+
+    @staticmethod
+    def forward(ctx, spec, B, n_dense, *tensors):
+        dense = tensors[:n_dense]
+        wb = tensors[n_dense:]
+        layers = [(wb[2 * i], wb[2 * i + 1], spec.acts[i]) for i in range(len(wb) // 2)]
+        need = spec.save and any(t.requires_grad for t in tensors)
+        segments = spec.build_segments(dense)
+        res = ops.mlp_forward(segments, layers, B, out_ld=spec.out_ld, out_col0=spec.out_col0,
+                              copy_seg=spec.copy_seg, save=need, latent=spec.latent, eps=spec.eps,
+                              seed=spec.seed, offset=spec.offset)
+        ctx.spec, ctx.n_dense, ctx.n_layers = spec, n_dense, len(layers)
+        ctx.n_out = layers[-1][0].shape[0]
+        if need:
+            offs, o = [], 0
+            for s in segments:
+                offs.append(o)
+                o += s.width
+            ctx.seg_off = offs
+            ctx.seg_width = [s.width for s in segments]
+            saved = [res["x0"]] + res["acts"] + [res["out"]] + [w for (w, _, _) in layers]
+            if spec.latent:
+                saved.append(res["eps"])
+            ctx.save_for_backward(*saved)
+        if spec.latent:
+            return res["out"], res["z"]
+        return res["out"]
+
+    @staticmethod
+    def backward(ctx, d_out, d_z=None):
+        spec, nl = ctx.spec, ctx.n_layers
+        saved = ctx.saved_tensors
+        x0, acts, out = saved[0], saved[1:nl], saved[nl]
+        Ws = saved[nl + 1:nl + 1 + nl]
+        c0 = spec.out_col0
+        g = None
+        if d_out is not None:
+            g = d_out[:, c0:c0 + ctx.n_out]
+        if spec.latent:
+            Z = spec.latent
+            if d_z is not None:
+                eps = saved[-1]
+                std = torch.exp(0.5 * out[:, c0 + Z:c0 + 2 * Z])
+                gz = torch.cat([d_z, d_z * eps * 0.5 * std], 1)
+                g = gz if g is None else g + gz
+        if g is None:
+            return (None,) * (3 + ctx.n_dense + 2 * nl)
+        g = g.contiguous()
+        grads_wb = [None] * (2 * nl)
+        for l in range(nl - 1, -1, -1):
+            a_out = out[:, c0:c0 + ctx.n_out] if l == nl - 1 else acts[l]
+            g = _act_grad(g, a_out, spec.acts[l])
+            a_prev = x0 if l == 0 else acts[l - 1]
+            grads_wb[2 * l] = g.t().mm(a_prev)
+            grads_wb[2 * l + 1] = g.sum(0)
+            g = g.mm(Ws[l])
+        d_dense = [None] * ctx.n_dense
+        for si, s in enumerate(spec.segs):
+            if s[0] == "dense" and ctx.needs_input_grad[3 + s[1]]:
+                o = ctx.seg_off[si]
+                d_dense[s[1]] = g[:, o:o + ctx.seg_width[si]]
+        return (None, None, None, *d_dense, *grads_wb)
+
+
+class CatalogCEFn(torch.autograd.Function):
+    """mean_i [ logsumexp_j(mask * <q_i, w_j>) - <q_i, w_{t_i}> ] over the whole catalog
+    (train_generative.py:36-42, 59) without materialising logits."""
+
+    @staticmethod
+    def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset):
+        loss_rows, lse, dq = ops.ce_fwd_bwd(table, q, targets, keep_prob, bitmask, seed, offset,
+                                            want_dq=q.requires_grad)
+        ctx.M = q.shape[0]
+        if dq is not None:
+            ctx.save_for_backward(dq)
+        ctx.mark_non_differentiable(lse)
+        return loss_rows.mean(), loss_rows, lse
+
+    @staticmethod
+    def backward(ctx, g_mean, g_rows, _g_lse):
+        (dq,) = ctx.saved_tensors
+        scale = g_mean / ctx.M
+        d = dq * scale
+        if g_rows is not None:
+            d = d + dq * g_rows.unsqueeze(1)
+        return d, None, None, None, None, None, None
+
+
+class KLFn(torch.autograd.Function):
+    """-0.5 * sum(1 + lv - plv - (exp(lv) + (mu-pmu)^2)/exp(plv))  (train_generative.py:61)."""
+
+    @staticmethod
+    def forward(ctx, mu, lv, pmu, plv):
+        out, g = ops.kl_fwd_bwd(mu, lv, pmu, plv, grads=True)
+        ctx.save_for_backward(*g)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        return tuple(go * g for g in ctx.saved_tensors)
+
+
+class LogitsFn(torch.autograd.Function):
+    """p = q @ W^T materialised, for forward()'s API parity (pivotcvae.py:274)."""
+
+    @staticmethod
+    def forward(ctx, q, table):
+        ctx.table = table
+        return ops.score_logits(table, q)
+
+    @staticmethod
+    def backward(ctx, dp):
+        return dp.mm(ctx.table.weight), None

@@ -1,0 +1,152 @@
+"""User-response simulators — drop-in for the reference's env/response_model.py.
+
+sample_users (:10-13), Environment (:15-38), UserResponseModel_MLP (:47-87),
+URM (:97-154), URM_P (:264-302), URM_P_MR (:305-323).  Forward passes run in
+libpcv_b200 (fused gather+normalise+MLP, gather-plus-dot); construction and the
+parameter containers stay torch so reference checkpoints load.
+"""
+import math
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import ops
+
+
+def sample_users(environment, batch_size):
+    """Uniform user ids (response_model.py:10-13).  The reference draws on the CPU with
+    torch.multinomial(ones) and copies; here the draw happens on the device."""
+    dev = torch.device(environment.device)
+    return torch.randint(0, environment.maxUserId + 1, (batch_size,), device=dev, dtype=torch.int64)
+
+
+class Environment(nn.Module):
+    def __init__(self, maxIID, maxUID, f_size, s_size, device, no_user):
+        super().__init__()
+        self.maxItemId, self.maxUserId = maxIID, maxUID
+        self.featureSize, self.slateSize = f_size, s_size
+        self.device = device
+        self.noUser = no_user
+        a = math.sqrt(2.0 / f_size)
+        self.docEmbed = nn.Embedding(maxIID + 1, f_size)
+        self.docEmbed.weight.data.uniform_(-a, a)
+        if not no_user:
+            self.userEmbed = nn.Embedding(maxUID + 1, f_size)
+            self.userEmbed.weight.data.uniform_(-a, a)
+
+    def _ids(self, slates, users):
+        dev = self.docEmbed.weight.device
+        if dev.type != "cuda":
+            raise L.PcvError("response models run on a B200 only: move the module with .to('cuda:0')")
+        slates = slates.to(dev, torch.int64)
+        users = users.to(dev, torch.int64).reshape(-1) if users is not None else None
+        return slates, users
+
+
+class UserResponseModel_MLP(Environment):
+    def __init__(self, maxIID, maxUID, f_size, s_size, struct, device, no_user):
+        super().__init__(maxIID, maxUID, f_size, s_size, device, no_user)
+        assert struct[0] == (s_size if no_user else s_size + 1) * f_size
+        assert struct[-1] == s_size
+        self.mlp = []
+        for i in range(len(struct) - 1):
+            m = nn.Linear(struct[i], struct[i + 1])
+            nn.init.kaiming_uniform_(m.weight)
+            self.mlp.append(m)
+            self.add_module("mlp_%d" % (i + 1), m)
+
+    def forward(self, slates, users):
+        """gather L rows -> L2-normalise the flattened slate vector -> [+ normalised user row]
+        -> Linear/ReLU chain -> (B, L) logits (response_model.py:76-87); one fused kernel."""
+        slates, users = self._ids(slates, users)
+        B = slates.shape[0]
+        segs = [ops.Gather(self.docEmbed.weight.detach(), slates.reshape(B, -1), normalize=True)]
+        if not self.noUser:
+            segs.append(ops.Gather(self.userEmbed.weight.detach(), users.reshape(B, 1), normalize=True))
+        n = len(self.mlp)
+        layers = [(m.weight.detach(), m.bias.detach(), L.ACT_RELU if i < n - 1 else L.ACT_NONE)
+                  for i, m in enumerate(self.mlp)]
+        return ops.mlp_forward(segs, layers, B)["out"]
+
+
+class URM(Environment):
+    variant = L.URM
+
+    def __init__(self, maxIID, maxUID, slate_size, latent_size, device, no_user):
+        super().__init__(maxIID, maxUID, latent_size, slate_size, device, no_user)
+        assert not no_user
+        self.maxIID = torch.tensor(maxIID)
+        self.maxUID = torch.tensor(maxUID)
+        self.itemBias = nn.Embedding(maxIID + 1, 1)
+        self.itemBias.weight.data.zero_()
+        self.userBias = nn.Embedding(maxUID + 1, 1)
+        self.userBias.weight.data.zero_()
+        self.m = nn.Sigmoid()
+
+    def to(self, *args, **kwargs):
+        out = super().to(*args, **kwargs)
+        out.device = args[0] if args else kwargs.get("device", out.device)
+        return out
+
+    def _extra(self):
+        return {}
+
+    def forward(self, slates, users):
+        """(B, L) click scores: sigmoid(<norm(d), u> + b_i + b_u) [+ positional / relation terms]."""
+        slates, users = self._ids(slates, users)
+        return ops.urm_forward(self.variant, self.docEmbed.weight.detach(), self.userEmbed.weight.detach(),
+                               self.itemBias.weight.detach(), self.userBias.weight.detach(), slates, users,
+                               **self._extra())
+
+    def core_forward(self, slates, users):
+        """5-tuple of the reference (response_model.py:129-150); the auxiliary tensors are plain gathers."""
+        slates_d, users_d = self._ids(slates, users)
+        p = self.forward(slates, users)
+        B = slates_d.shape[0]
+        dEmb = torch.nn.functional.normalize(self.docEmbed.weight[slates_d], p=2, dim=-1).view(B, self.slateSize, -1)
+        dBias = self.itemBias.weight[slates_d].view(B, self.slateSize)
+        return p, dEmb, dBias, self.userEmbed.weight[users_d], self.userBias.weight[users_d]
+
+    def sample_response(self, slate_p):
+        """threshold at 0.5 (response_model.py:156-169)."""
+        return (slate_p >= 0.5).to(slate_p.dtype)
+
+    def generate_response_for_dataset(self, sampledU, sampledSlates):
+        with torch.no_grad():
+            return self.sample_response(self.forward(sampledSlates, sampledU.reshape(-1)))
+
+
+class URM_P(URM):
+    variant = L.URM_P
+
+    def __init__(self, maxIID, maxUID, slate_size, latent_size, device, no_user, p_bias_max, p_bias_min):
+        super().__init__(maxIID, maxUID, slate_size, latent_size, device, no_user)
+        self.p_bias_max, self.p_bias_min = p_bias_max, p_bias_min
+        self.posBias = torch.tensor([p_bias_max - i * (p_bias_max - p_bias_min) / slate_size
+                                     for i in range(slate_size)])
+        a = math.sqrt(0.5 / latent_size)
+        self.posDependentBias = torch.FloatTensor(slate_size * latent_size).uniform_(-a, a).reshape(slate_size, latent_size)
+
+    def to(self, *args, **kwargs):
+        out = super().to(*args, **kwargs)
+        out.posBias = out.posBias.to(args[0])
+        out.posDependentBias = out.posDependentBias.to(args[0])
+        return out
+
+    def _extra(self):
+        dev = self.docEmbed.weight.device
+        return dict(pos_bias=self.posBias.to(dev), pos_dep=self.posDependentBias.to(dev))
+
+
+class URM_P_MR(URM_P):
+    variant = L.URM_P_MR
+
+    def __init__(self, maxIID, maxUID, slate_size, latent_size, device, no_user, p_bias_max, p_bias_min, mr_factor):
+        super().__init__(maxIID, maxUID, slate_size, latent_size, device, no_user, p_bias_max, p_bias_min)
+        self.mrFactor = mr_factor
+
+    def _extra(self):
+        e = super()._extra()
+        e["mr_factor"] = float(self.mrFactor)
+        return e

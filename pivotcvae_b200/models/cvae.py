@@ -1,0 +1,215 @@
+"""BaseCVAE — drop-in for the reference's models/cvae.py:7-118, running on libpcv_b200.
+
+Same constructor, attributes (docEmbed, userEmbed, slate_size, latent_size,
+noUser, device, candidateFlag) and methods (reparametrize, get_condition,
+get_recommended_item, sample_encoding); the arithmetic is the sm_100a kernels.
+"""
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import ops
+from ..autograd import FusedMLPFn, MlpSpec
+from ..noise import NoiseSource
+
+
+def _require_cuda(device):
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise L.PcvError("pivotcvae_b200 models run on a B200 only (device=%r); there is no CPU path" % (device,))
+    return dev
+
+
+class BaseCVAE(nn.Module):
+    def __init__(self, embeddings, u_embeddings, slate_size, latent_size, no_user, device, fine_tune=False):
+        super().__init__()
+        self.candidateFlag = False
+        self.slate_size = slate_size
+        self.latent_size = latent_size
+        self.noUser = no_user
+        self.device = device
+        dev = _require_cuda(device)
+        # frozen, row-L2-normalised copies of the pretrained tables (cvae.py:27-41)
+        with torch.no_grad():
+            src = embeddings.weight.detach().to(dev, torch.float32)
+            self.docEmbed = nn.Embedding(src.shape[0], src.shape[1], device=dev)
+            self.docEmbed.weight.data.copy_(ops.normalize_rows(src))
+            self.docEmbed.weight.requires_grad = fine_tune
+            if not no_user:
+                usrc = u_embeddings.weight.detach().to(dev, torch.float32)
+                self.userEmbed = nn.Embedding(usrc.shape[0], usrc.shape[1], device=dev)
+                self.userEmbed.weight.data.copy_(ops.normalize_rows(usrc))
+                self.userEmbed.weight.requires_grad = fine_tune
+        if fine_tune:
+            raise L.PcvError("fine_tune=True is not supported: the fused kernels treat the tables as frozen "
+                             "(every reference subclass hard-codes fine_tune=False)")
+        self.noise = NoiseSource()
+        self.select_engine = "auto"
+        self._table = None
+
+    # ---- extension state is rebuilt lazily (whole-model pickling, train_generative.py:199)
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_table"] = None
+        return st
+
+    def _apply(self, fn, *a, **k):
+        self._table = None
+        return super()._apply(fn, *a, **k)
+
+    def item_table(self):
+        w = self.docEmbed.weight
+        t = self._table
+        if t is None or t.weight.data_ptr() != w.data_ptr() or t.n_rows != w.shape[0]:
+            t = ops.Table(w.detach())
+            self._table = t
+        return t
+
+    # ---- helpers shared by the subclasses
+    @staticmethod
+    def _stack(mods, hidden_act, last_act):
+        """[(W, b, act)] for a list of nn.Linear."""
+        n = len(mods)
+        return [(m.weight, m.bias, hidden_act if i < n - 1 else last_act) for i, m in enumerate(mods)]
+
+    def _heads(self, mu_lin, lv_lin):
+        """The two latent heads as ONE linear layer emitting [mu | logvar]."""
+        return torch.cat([mu_lin.weight, lv_lin.weight], 0), torch.cat([mu_lin.bias, lv_lin.bias], 0)
+
+    def _run_block(self, segs, layers, B, dense=(), **kw):
+        """One fused MLP block; differentiable when grad mode is on."""
+        spec = MlpSpec(segs, [a for (_, _, a) in layers], save=torch.is_grad_enabled(), **kw)
+        flat = []
+        for (W, b, _) in layers:
+            flat += [W, b]
+        return FusedMLPFn.apply(spec, B, len(dense), *dense, *flat)
+
+    def _user_seg(self, u):
+        return ("gather", self.userEmbed.weight, u.reshape(-1, 1))
+
+    def _eps_args(self, B):
+        eps = self.noise.pop("eps")
+        if eps is not None:
+            return dict(eps=eps.to(self.docEmbed.weight.device))
+        seed, off = self.noise.next_stream(B)
+        return dict(seed=seed, offset=off)
+
+    # ---- reference API
+    def encode(self, emb, c, u_emb=None):
+        raise NotImplementedError
+
+    def decode(self, z, c, u_emb=None):
+        raise NotImplementedError
+
+    def get_prior(self, r, u=None):
+        raise NotImplementedError
+
+    def forward(self, s, r, candidates=None, u=None):
+        raise NotImplementedError
+
+    def recommend(self, r, u=None, return_item=False):
+        raise NotImplementedError
+
+    def log(self, logger):
+        raise NotImplementedError
+
+    def reparametrize(self, mu, logvar):
+        """z = eps * exp(0.5*logvar) + mu (cvae.py:79-83); eps from the model's NoiseSource.
+        Runs the kernel's reparameterisation epilogue behind an identity layer."""
+        B, Z = mu.shape
+        x = torch.cat([mu, logvar], 1)
+        eye = torch.eye(2 * Z, device=x.device)
+        _, z = self._run_block([("dense", 0)], [(eye, torch.zeros(2 * Z, device=x.device), L.ACT_NONE)], B,
+                               dense=(x,), latent=Z, **self._eps_args(B))
+        return z
+
+    def get_condition(self, r):
+        """one-hot of the number of clicks (cvae.py:85-92)."""
+        r = r.to(self.docEmbed.weight.device, torch.float32)
+        B, Ls = r.shape
+        eye = torch.eye(Ls + 1, device=r.device)
+        res = ops.mlp_forward([ops.OneHot(r)], [(eye, torch.zeros(Ls + 1, device=r.device), L.ACT_NONE)], B)
+        return res["out"]
+
+    def get_recommended_item(self, embeddings):
+        """arg-max item per row over the whole catalog (cvae.py:97-101) -> int64 (rows,)."""
+        q = embeddings.reshape(-1, self.feature_size)
+        idx, _ = ops.score_select(self.item_table(), q.detach(), "greedy", engine=self.select_engine, want_val=False)
+        return idx
+
+    def sample_encoding(self, s, r, u=None):
+        """encoder only (cvae.py:103-115) -> (z_mu, z_logvar)."""
+        out = self._encode_ids(s, r, u)
+        Z = self.latent_size
+        return out[:, :Z], out[:, Z:]
+
+    # ---- fused blocks shared by PivotCVAE and ListCVAE ----------------------
+    def _dev(self):
+        return self.docEmbed.weight.device
+
+    def _inputs(self, r=None, u=None, s=None):
+        dev = self._dev()
+        if r is not None:
+            r = r.to(dev, torch.float32)
+        if u is not None:
+            u = u.to(dev, torch.int64).reshape(-1)
+        if s is not None:
+            s = s.to(dev, torch.int64)
+        return r, u, s
+
+    def _build_mlp(self, prefix, struct):
+        """nn.Linear chain registered as <prefix>_1.. (same names/init as the reference,
+        pivotcvae.py:108-113) so reference state_dicts load."""
+        mods = []
+        for i in range(len(struct) - 1):
+            m = nn.Linear(struct[i], struct[i + 1])
+            nn.init.kaiming_uniform_(m.weight)
+            self.add_module("%s_%d" % (prefix, i + 1), m)
+            mods.append(m)
+        return mods
+
+    def _prior_block(self, r, u, reparam):
+        """[onehot(r), user] -> prior_i (LeakyReLU each) -> [mu | logvar] (+ z).
+        pivotcvae.py:229-240 / 279-290, listcvae.py:121-132 / 171-182."""
+        segs = [("onehot", r)] + ([] if self.noUser else [self._user_seg(u)])
+        layers = self._stack(self.priorMLP, L.ACT_LEAKY, L.ACT_LEAKY)
+        hw, hb = self._heads(self.priorMu, self.priorLogvar)
+        layers.append((hw, hb, L.ACT_NONE))
+        B = r.shape[0]
+        if reparam:
+            return self._run_block(segs, layers, B, latent=self.latent_size, **self._eps_args(B))
+        return self._run_block(segs, layers, B), None
+
+    def _encode_ids(self, s, r, u, reparam=False):
+        """[docEmbed(s), onehot(r), user] -> enc_i (LeakyReLU each) -> [mu | logvar] (+ z).
+        pivotcvae.py:250-260, 159-174."""
+        r, u, s = self._inputs(r, u, s)
+        segs = [("gather", self.docEmbed.weight, s), ("onehot", r)] + ([] if self.noUser else [self._user_seg(u)])
+        layers = self._stack(self.encMLP, L.ACT_LEAKY, L.ACT_LEAKY)
+        hw, hb = self._heads(self.encmu, self.enclogvar)
+        layers.append((hw, hb, L.ACT_NONE))
+        B = s.shape[0]
+        if reparam:
+            return self._run_block(segs, layers, B, latent=self.latent_size, **self._eps_args(B))
+        return self._run_block(segs, layers, B)
+
+    def encode(self, emb, c, u_emb=None):
+        """Q(z|s) on already-gathered tensors (pivotcvae.py:159-174) -> (z_mu, z_logvar)."""
+        dense = [emb, c] + ([] if self.noUser else [u_emb])
+        segs = [("dense", i) for i in range(len(dense))]
+        layers = self._stack(self.encMLP, L.ACT_LEAKY, L.ACT_LEAKY)
+        hw, hb = self._heads(self.encmu, self.enclogvar)
+        layers.append((hw, hb, L.ACT_NONE))
+        out = self._run_block(segs, layers, emb.shape[0], dense=tuple(dense))
+        Z = self.latent_size
+        return out[:, :Z], out[:, Z:]
+
+    def get_prior(self, r, u=None):
+        r, u, _ = self._inputs(r, u)
+        out, _ = self._prior_block(r, u, reparam=False)
+        Z = self.latent_size
+        return out[:, :Z], out[:, Z:]
+
+    def _logits(self, rx_flat):
+        from ..autograd import LogitsFn
+        return LogitsFn.apply(rx_flat, self.item_table())

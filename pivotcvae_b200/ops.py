@@ -1,0 +1,357 @@
+"""Torch-facing wrappers of the C ABI: tensors in, tensors out, current CUDA stream.
+
+torch is plumbing here (device memory, streams, autograd bookkeeping); all the
+arithmetic of the hot path happens in libpcv_b200.so.  Every function raises if
+handed a non-CUDA tensor — there is no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class KernelTimer:
+    """CUDA-event timing of individual library calls on the launching stream
+    (bench.py's roofline leg).  Usage: with ops.KernelTimer() as kt: ...; kt.summary()."""
+
+    active = None
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            tot, n = out.get(name, (0.0, 0))
+            out[name] = (tot + a.elapsed_time(b), n + 1)
+        return {k: {"ms_total": v[0], "calls": v[1], "ms_avg": v[0] / v[1]} for k, v in out.items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        kt = KernelTimer.active
+        if kt is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        kt = KernelTimer.active
+        if kt is not None:
+            self.b.record()
+            kt.events.append((self.name, self.a, self.b))
+
+
+def _req(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise L.PcvError("%s must be a CUDA tensor (libpcv_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _f32(t, name="tensor"):
+    return _req(t, torch.float32, name)
+
+
+def _i64(t, name="index tensor"):
+    return _req(t, torch.int64, name)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def launch_count():
+    return int(L.load().pcv_launch_count())
+
+
+def device_ok(device=None):
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    L.check(L.load().pcv_device_ok(dev), "pcv_device_ok")
+    return True
+
+
+# ----------------------------------------------------------------------------
+# item table handle
+# ----------------------------------------------------------------------------
+class Table:
+    """Borrowed view of the frozen item table (cvae.py:30-32) + cached workspaces."""
+
+    def __init__(self, weight, row_offset=0):
+        self.weight = _f32(weight, "item table")
+        if self.weight.dim() != 2:
+            raise L.PcvError("item table must be 2-D")
+        self.n_rows, self.dim = self.weight.shape
+        self.row_offset = int(row_offset)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.weight.device):
+            L.check(L.load().pcv_table_create(_ptr(self.weight), self.n_rows, self.dim, self.row_offset,
+                                              ctypes.byref(self._h)), "pcv_table_create")
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.load().pcv_table_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace(self, kind, M):
+        key = (kind, int(M))
+        ws = self._ws.get(key)
+        if ws is None:
+            n = ctypes.c_size_t()
+            fn = L.load().pcv_score_select_workspace_bytes if kind == "select" else L.load().pcv_ce_workspace_bytes
+            L.check(fn(self._h, int(M), ctypes.byref(n)), "workspace query")
+            ws = torch.empty(max(int(n.value), 256), dtype=torch.uint8, device=self.weight.device)
+            if len(self._ws) > 16:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+
+def normalize_rows(W):
+    W = _f32(W, "W")
+    out = torch.empty_like(W)
+    with torch.cuda.device(W.device):
+        L.check(L.load().pcv_normalize_rows(_ptr(W), W.shape[0], W.shape[1], _ptr(out), _stream()), "pcv_normalize_rows")
+    return out
+
+
+# ----------------------------------------------------------------------------
+# score + select
+# ----------------------------------------------------------------------------
+def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="auto", want_val=True):
+    """-> (idx int64[M], val f32[M]).  mode 'greedy' | 'exprace'."""
+    Q = _f32(Q, "Q")
+    M, D = Q.shape
+    if D != table.dim:
+        raise L.PcvError("Q has dim %d, table has dim %d" % (D, table.dim))
+    opts = L.SelectOpts()
+    opts.mode = L.SELECT_GREEDY if mode == "greedy" else L.SELECT_EXPRACE
+    opts.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
+    if noise is not None:
+        noise = _f32(noise, "noise")
+        if tuple(noise.shape) != (M, table.n_rows):
+            raise L.PcvError("noise must be [M, n_rows]")
+    opts.noise = noise.data_ptr() if noise is not None else None
+    opts.seed, opts.offset, opts.no_repeat = int(seed), int(offset), 0
+    idx = torch.empty(M, dtype=torch.int64, device=Q.device)
+    val = torch.empty(M, dtype=torch.float32, device=Q.device) if want_val else None
+    ws = table.workspace("select", M)
+    with torch.cuda.device(Q.device), _timed("score_select_%s_M%d" % (mode, M)):
+        L.check(L.load().pcv_score_select(table.handle, _ptr(Q), M, ctypes.byref(opts), _ptr(idx), _ptr(val),
+                                          _ptr(ws), ws.numel(), _stream()), "pcv_score_select")
+    return idx, val
+
+
+def score_logits(table, Q):
+    Q = _f32(Q, "Q")
+    out = torch.empty(Q.shape[0], table.n_rows, dtype=torch.float32, device=Q.device)
+    with torch.cuda.device(Q.device):
+        L.check(L.load().pcv_score_logits(table.handle, _ptr(Q), Q.shape[0], _ptr(out), _stream()), "pcv_score_logits")
+    return out
+
+
+def philox_exponential(seed, offset, M, n_cols, device, col_offset=0):
+    out = torch.empty(M, n_cols, dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        L.check(L.load().pcv_philox_exponential(int(seed), int(offset), M, n_cols, col_offset, _ptr(out), _stream()),
+                "pcv_philox_exponential")
+    return out
+
+
+def vp_merge_select(vals, idx):
+    """vals/idx: [G, M] partial winners in shard order -> (idx[M], val[M])."""
+    vals, idx = _f32(vals, "vals"), _i64(idx, "idx")
+    G, M = vals.shape
+    oi = torch.empty(M, dtype=torch.int64, device=vals.device)
+    ov = torch.empty(M, dtype=torch.float32, device=vals.device)
+    with torch.cuda.device(vals.device):
+        L.check(L.load().pcv_vp_merge_select(_ptr(vals), _ptr(idx), G, M, _ptr(oi), _ptr(ov), _stream()),
+                "pcv_vp_merge_select")
+    return oi, ov
+
+
+# ----------------------------------------------------------------------------
+# fused MLP block
+# ----------------------------------------------------------------------------
+class Dense:
+    def __init__(self, t):
+        self.t = _f32(t, "dense segment")
+        self.width = self.t.shape[1]
+
+    def fill(self, seg, keep):
+        seg.kind, seg.ptr, seg.idx = L.SEG_DENSE, self.t.data_ptr(), None
+        seg.width, seg.count, seg.norm = self.width, 1, L.NORM_NONE
+        keep.append(self.t)
+
+
+class OneHot:
+    """one-hot(sum_l r[b, l]) of width L+1 (cvae.py:85-92)."""
+
+    def __init__(self, r):
+        self.r = _f32(r, "responses")
+        self.width = self.r.shape[1] + 1
+
+    def fill(self, seg, keep):
+        seg.kind, seg.ptr, seg.idx = L.SEG_ONEHOT, self.r.data_ptr(), None
+        seg.width, seg.count, seg.norm = self.width, self.r.shape[1], L.NORM_NONE
+        keep.append(self.r)
+
+
+class Gather:
+    """rows table[idx[b, :]] concatenated (nn.Embedding lookups, pivotcvae.py:253)."""
+
+    def __init__(self, table, idx, normalize=False):
+        self.table = _f32(table, "gather table")
+        idx = _i64(idx, "gather index")
+        self.idx = idx.reshape(idx.shape[0], -1)
+        self.count = self.idx.shape[1]
+        self.width = self.count * self.table.shape[1]
+        self.normalize = normalize
+
+    def fill(self, seg, keep):
+        seg.kind, seg.ptr, seg.idx = L.SEG_GATHER, self.table.data_ptr(), self.idx.data_ptr()
+        seg.width, seg.count = self.table.shape[1], self.count
+        seg.norm = L.NORM_SEGMENT if self.normalize else L.NORM_NONE
+        keep.extend([self.table, self.idx])
+
+
+def mlp_forward(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
+                latent=0, eps=None, seed=0, offset=0):
+    """Run one fused MLP block.
+
+    segments: list of Dense/OneHot/Gather; layers: list of (W[n_out,n_in], b[n_out], act).
+    Returns dict(out=..., z=..., eps=..., x0=..., acts=[...]) (entries present when requested).
+    """
+    if len(segments) > L.PCV_MAX_SEGMENTS or len(layers) > L.PCV_MAX_LAYERS:
+        raise L.PcvError("too many segments / layers for one fused block")
+    d = L.MlpDesc()
+    keep = []
+    d.n_segments = len(segments)
+    for i, s in enumerate(segments):
+        s.fill(d.seg[i], keep)
+    n_in0 = sum(s.width for s in segments)
+    d.n_layers = len(layers)
+    prev = n_in0
+    dev = None
+    for i, (W, b, act) in enumerate(layers):
+        W, b = _f32(W, "weight"), _f32(b, "bias")
+        dev = W.device
+        d.layer[i].W, d.layer[i].b = W.data_ptr(), b.data_ptr()
+        d.layer[i].n_in, d.layer[i].n_out, d.layer[i].act = W.shape[1], W.shape[0], act
+        keep.extend([W, b])
+        prev = W.shape[0]
+    n_out = prev
+    if out is None:
+        out_ld = out_col0 + n_out if out_ld is None else out_ld
+        out = torch.empty(B, out_ld, dtype=torch.float32, device=dev)
+    d.out, d.out_ld, d.out_col0, d.copy_seg = out.data_ptr(), int(out_ld), int(out_col0), int(copy_seg)
+    res = {"out": out}
+    if save:
+        x0 = torch.empty(B, n_in0, dtype=torch.float32, device=dev)
+        d.x0 = x0.data_ptr()
+        acts = []
+        for i, (W, _, _) in enumerate(layers[:-1]):
+            a = torch.empty(B, W.shape[0], dtype=torch.float32, device=dev)
+            d.acts[i] = a.data_ptr()
+            acts.append(a)
+        res["x0"], res["acts"] = x0, acts
+    d.latent = int(latent)
+    if latent:
+        z = torch.empty(B, latent, dtype=torch.float32, device=dev)
+        d.z = z.data_ptr()
+        res["z"] = z
+        if eps is not None:
+            eps = _f32(eps, "eps")
+            d.eps = eps.data_ptr()
+            keep.append(eps)
+            res["eps"] = eps
+        else:
+            eo = torch.empty(B, latent, dtype=torch.float32, device=dev)
+            d.eps_out = eo.data_ptr()
+            res["eps"] = eo
+        d.seed, d.offset = int(seed), int(offset)
+    with torch.cuda.device(dev), _timed("mlp_fwd"):
+        L.check(L.load().pcv_mlp_fwd(ctypes.byref(d), int(B), _stream()), "pcv_mlp_fwd")
+    return res
+
+
+# ----------------------------------------------------------------------------
+# KL, CE, response models
+# ----------------------------------------------------------------------------
+def kl_fwd_bwd(mu, logvar, pmu, plogvar, grads=True):
+    mu, logvar, pmu, plogvar = (_f32(t) for t in (mu, logvar, pmu, plogvar))
+    out = torch.empty((), dtype=torch.float32, device=mu.device)
+    g = [torch.empty_like(mu) for _ in range(4)] if grads else [None] * 4
+    with torch.cuda.device(mu.device):
+        L.check(L.load().pcv_kl_fwd_bwd(_ptr(mu), _ptr(logvar), _ptr(pmu), _ptr(plogvar), mu.numel(), _ptr(out),
+                                        _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _stream()), "pcv_kl_fwd_bwd")
+    return out, g
+
+
+def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0, want_dq=True):
+    """-> (loss_rows[M], lse[M], dq[M, D] or None); see include/pcv_b200.h."""
+    Q, targets = _f32(Q, "Q"), _i64(targets, "targets").reshape(-1)
+    M, D = Q.shape
+    mask = L.CeMask()
+    mask.keep_prob = float(keep_prob)
+    if bitmask is not None:
+        if not bitmask.is_cuda:
+            raise L.PcvError("bitmask must be a CUDA tensor")
+        bitmask = bitmask.contiguous()
+        if bitmask.dtype not in (torch.int32, torch.uint32) or tuple(bitmask.shape) != (M, (table.n_rows + 31) // 32):
+            raise L.PcvError("bitmask must be int32/uint32 [M, ceil(N/32)]")
+        mask.bitmask = bitmask.data_ptr()
+    mask.seed, mask.offset = int(seed), int(offset)
+    loss = torch.empty(M, dtype=torch.float32, device=Q.device)
+    lse = torch.empty(M, dtype=torch.float32, device=Q.device)
+    dq = torch.empty(M, D, dtype=torch.float32, device=Q.device) if want_dq else None
+    ws = table.workspace("ce", M)
+    with torch.cuda.device(Q.device), _timed("ce_fwd_bwd"):
+        L.check(L.load().pcv_ce_fwd_bwd(table.handle, _ptr(Q), _ptr(targets), M, ctypes.byref(mask), _ptr(loss),
+                                        _ptr(lse), _ptr(dq), _ptr(ws), ws.numel(), _stream()), "pcv_ce_fwd_bwd")
+    return loss, lse, dq
+
+
+def urm_forward(variant, doc, usr, item_bias, user_bias, slates, users, pos_bias=None, pos_dep=None, mr_factor=0.0):
+    doc, usr = _f32(doc), _f32(usr)
+    ib, ub = _f32(item_bias).reshape(-1), _f32(user_bias).reshape(-1)
+    slates, users = _i64(slates), _i64(users).reshape(-1)
+    B, Ls = slates.shape
+    d = L.UrmDesc()
+    d.variant = variant
+    d.doc_table, d.user_table, d.item_bias, d.user_bias = doc.data_ptr(), usr.data_ptr(), ib.data_ptr(), ub.data_ptr()
+    keep = [doc, usr, ib, ub]
+    if pos_bias is not None:
+        pb, pd = _f32(pos_bias).reshape(-1), _f32(pos_dep).reshape(-1)
+        d.pos_bias, d.pos_dep = pb.data_ptr(), pd.data_ptr()
+        keep += [pb, pd]
+    d.mr_factor, d.L, d.D = float(mr_factor), Ls, doc.shape[1]
+    out = torch.empty(B, Ls, dtype=torch.float32, device=doc.device)
+    with torch.cuda.device(doc.device):
+        L.check(L.load().pcv_urm_fwd(ctypes.byref(d), _ptr(slates), _ptr(users), B, _ptr(out), _stream()), "pcv_urm_fwd")
+    return out

@@ -1,0 +1,151 @@
+"""Training / evaluation driver — drop-in for the reference's train_generative.py.
+
+downsample (:36-42), get_gen_loss (:44-65), train_on_dataset (:67-214),
+get_model (:221-240), add_gen_model_parse (:301-318).  get_gen_loss routes the
+reconstruction term through the fused catalog cross-entropy so the (B*L, N)
+logits, the mask and the soft-max never reach HBM; everything else keeps the
+reference's semantics (CE mean over B*L rows, KL summed, Adam without decay).
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .autograd import CatalogCEFn, KLFn
+from .env.response_model import sample_users
+from .models.listcvae import UserListCVAEWithPrior
+from .models.pivotcvae import PIVOTCVAE_MODELS
+
+
+def downsample(pred, slate, n_neg=1000.0):
+    """pred * (onehot(target) U Bernoulli(n_neg/N)) on a materialised logit matrix
+    (train_generative.py:36-42).  Kept for API parity; training never calls it."""
+    mask = torch.bernoulli(torch.full_like(pred, n_neg / pred.shape[1]))
+    mask.scatter_(1, slate.reshape(-1, 1), 1.0)
+    return pred * mask
+
+
+def _as_tensor(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype, device=device)
+
+
+def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
+    """-> (loss, recLoss, KLD) with autograd attached (train_generative.py:44-65).
+
+    lossFun is accepted for signature parity; the reconstruction term is always the
+    mean soft-max CE the reference builds with nn.CrossEntropyLoss (:105)."""
+    dev = model.docEmbed.weight.device
+    slates = _as_tensor(batch_data["slates"], torch.int64, dev)
+    users = _as_tensor(batch_data["users"], torch.int64, dev)
+    targets = _as_tensor(batch_data["responses"], torch.float32, dev)
+    pMu, pLogvar = model.get_prior(targets, users)
+    if model.candidateFlag:
+        raise NotImplementedError("candidate-mode training is SURVEY §8(f) N1: not built yet (use --mask_train)")
+    rx, z, mu, logvar, _ = model.forward_latent(slates, targets, users)
+    table = model.item_table()
+    N = table.n_rows
+    if n_neg > N:
+        raise RuntimeError("n_neg (%d) > number of items (%d): torch.bernoulli would reject p > 1" % (n_neg, N))
+    keep = float(n_neg) / float(N)
+    bitmask = model.noise.pop("mask")
+    M = slates.numel()
+    seed, off = (0, 0)
+    if bitmask is None and keep < 1.0:
+        seed, off = model.noise.next_stream(M)
+    recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, seed, off)
+    KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
+    loss = recLoss + beta * KLD
+    return loss, recLoss, KLD
+
+
+def recommendation_test(model, resp_model, bs, n_trial=100, n_context=5):
+    """The per-epoch 100 x 5 recommendation test (train_generative.py:168-195):
+    -> (min, mean, max) expected click counts per context, each (n_context,)."""
+    enc = torch.zeros(n_context, n_trial)
+    maxnc = torch.zeros(n_context, n_trial)
+    minnc = torch.zeros(n_context, n_trial)
+    dev = model.docEmbed.weight.device
+    with torch.no_grad():
+        for k in range(n_trial):
+            users = sample_users(resp_model, bs)
+            context = torch.zeros(bs, n_context, device=dev)
+            stats = []
+            for i in range(n_context):
+                context[:, i] = 1
+                rSlates, _ = model.recommend(context, users, return_item=True)
+                resp = torch.sigmoid(resp_model(rSlates.view(bs, -1), users))
+                nc = resp.sum(1)
+                stats.append(torch.stack([nc.mean(), nc.max(), nc.min()]))
+            st = torch.stack(stats).cpu()  # one device->host sync per trial instead of 15
+            enc[:, k], maxnc[:, k], minnc[:, k] = st[:, 0], st[:, 1], st[:, 2]
+    return minnc.mean(1), enc.mean(1), maxnc.mean(1)
+
+
+def train_on_dataset(trainset, valset, model, model_path, logger, resp_model, bs, epochs, lr, decay, beta):
+    """Epoch loop of train_generative.py:67-214: Adam(lr) (no weight decay, F10), validation with
+    n_neg = trainset.nCandidate, recommendation test, save-best whole-model pickle."""
+    from torch.utils.data import DataLoader
+    trainLoader = DataLoader(trainset, batch_size=bs, shuffle=True, num_workers=0)
+    valLoader = DataLoader(valset, batch_size=bs, shuffle=False, num_workers=0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    trainHistory, valHistory = [], []
+    bestValLoss = float("inf")
+    for epoch in range(epochs):
+        logger.log("Epoch " + str(epoch + 1))
+        losses = []
+        for batchData in trainLoader:
+            optimizer.zero_grad()
+            loss, recLoss, kld = get_gen_loss(batchData, model, None, beta)
+            losses.append(loss.detach())
+            loss.backward()
+            optimizer.step()
+        trainHistory.append(float(torch.stack(losses).mean()))
+        logger.log("train loss: " + str(trainHistory[-1]))
+        vl, vr, vk = [], [], []
+        with torch.no_grad():
+            for batchData in valLoader:
+                loss, recLoss, KLD = get_gen_loss(batchData, model, None, beta, n_neg=trainset.nCandidate)
+                vl.append(loss)
+                vr.append(recLoss)
+                vk.append(KLD)
+        valHistory.append(float(torch.stack(vl).mean()))
+        logger.log("validation Loss: %s = %s + %s * %s" % (valHistory[-1], float(torch.stack(vr).mean()), beta,
+                                                           float(torch.stack(vk).mean())))
+        mn, me, mx = recommendation_test(model, resp_model, bs)
+        for i in range(len(me)):
+            logger.log("Expected response (%d): %s; %s; %s" % (i + 1, mn[i].numpy(), me[i].numpy(), mx[i].numpy()))
+        if epoch == 0 or valHistory[-1] < bestValLoss - 1e-3:
+            torch.save(model, open(model_path, "wb"))
+            logger.log("Save best model")
+            bestValLoss = valHistory[-1]
+    return trainHistory, valHistory
+
+
+def get_model(args, response_model):
+    """Factory of train_generative.py:221-240 (struct strings like "[54,256,256]")."""
+    parse = lambda s: [int(v) for v in s[1:-1].split(",")]
+    uemb = None if response_model.noUser else response_model.userEmbed
+    if args.model == "listcvae":
+        return UserListCVAEWithPrior(response_model.docEmbed, uemb, args.s, args.dim, args.z_size, args.s + 1,
+                                     parse(args.enc_struct), parse(args.dec_struct), parse(args.prior_struct),
+                                     args.nouser, args.device)
+    if args.model in PIVOTCVAE_MODELS:
+        return PIVOTCVAE_MODELS[args.model](response_model.docEmbed, uemb, args.s, args.dim, args.z_size, args.s + 1,
+                                            parse(args.enc_struct), parse(args.psm_struct), parse(args.scm_struct),
+                                            parse(args.prior_struct), args.nouser, args.device)
+    return None
+
+
+def add_gen_model_parse(parser):
+    parser.add_argument("--dim", type=int, default=8)
+    parser.add_argument("--model", type=str, default="pivotcvae_gt_pi")
+    parser.add_argument("--z_size", type=int, default=16)
+    parser.add_argument("--mask_train", action="store_true")
+    parser.add_argument("--enc_struct", type=str, default="[54,256,256]")
+    parser.add_argument("--prior_struct", type=str, default="[14,128,128]")
+    parser.add_argument("--beta", type=float, default=-1)
+    parser.add_argument("--dec_struct", type=str, default="[30,256,256,40]")
+    parser.add_argument("--psm_struct", type=str, default="[30,256,256,8]")
+    parser.add_argument("--scm_struct", type=str, default="[38,256,256,32]")
+    return parser

@@ -1,0 +1,199 @@
+"""-m gpu: the drop-in classes (reference API) against the reference's own outputs
+(golden fixtures) and against the CPU oracle, on identical weights / inputs / noise."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gpu_util import N, T, build_list, build_pivot, dev
+
+pytestmark = pytest.mark.gpu
+
+PIVOT_FIXTURES = ["pivot_small", "pivot_small_nouser", "pivot_c1"]
+
+
+def _users(fx):
+    return None if fx.cfg["no_user"] else T(fx["in/users"])
+
+
+@pytest.mark.parametrize("name", PIVOT_FIXTURES)
+def test_pivot_recommend_greedy_bitexact_slates(golden, name):
+    fx = golden(name)
+    m = build_pivot(fx)
+    cfg = fx.cfg
+    for k in (1, cfg["L"]):
+        tag = "rec_pi_k%d/" % k
+        m.noise.push("eps", T(fx[tag + "eps"]))
+        items, zmu = m.recommend(T(fx[tag + "ctx"]), _users(fx), return_item=True)
+        assert items.dtype == torch.int64 and items.shape == (cfg["B"] * cfg["L"],)
+        assert np.array_equal(N(items), fx[tag + "items"])          # == reference slates
+        np.testing.assert_allclose(N(zmu), fx[tag + "z_mu"], rtol=2e-5, atol=2e-6)
+        ref = oracle.pivot_recommend(fx.sub("sd/"), fx[tag + "ctx"], fx["in/users"], fx[tag + "eps"], cfg["no_user"])
+        assert np.array_equal(N(zmu), ref["z_mu"])                  # bitwise == oracle
+        m.noise.push("eps", T(fx[tag + "eps"]))
+        rx, _ = m.recommend(T(fx[tag + "ctx"]), _users(fx), return_item=False)
+        assert rx.shape == (cfg["B"], cfg["L"], cfg["D"])
+        assert np.array_equal(N(rx), ref["rx"])
+        np.testing.assert_allclose(N(rx), fx[tag + "rx"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", PIVOT_FIXTURES)
+def test_pivot_recommend_sampled_identical_rng(golden, name):
+    fx = golden(name)
+    m = build_pivot(fx, "pivotcvae_gt_spi")
+    tag = "rec_spi_k2/"
+    m.noise.push("eps", T(fx[tag + "eps"]))
+    m.noise.push("race", T(fx[tag + "noise"]))
+    items, _ = m.recommend(T(fx[tag + "ctx"]), _users(fx), return_item=True)
+    assert np.array_equal(N(items), fx[tag + "items"])
+
+
+@pytest.mark.parametrize("name", ["list_small", "list_small_user"])
+def test_list_recommend(golden, name):
+    fx = golden(name)
+    m = build_list(fx)
+    for k in (1, 3):
+        tag = "rec_k%d/" % k
+        m.noise.push("eps", T(fx[tag + "eps"]))
+        items, zmu = m.recommend(T(fx[tag + "ctx"]), _users(fx), return_item=True)
+        assert np.array_equal(N(items), fx[tag + "items"])
+        np.testing.assert_allclose(N(zmu), fx[tag + "z_mu"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", PIVOT_FIXTURES)
+@pytest.mark.parametrize("train,key", [("gt", "pivotcvae_gt_pi"), ("pt", "pivotcvae_pt_pi"),
+                                       ("spt", "pivotcvae_spt_pi"), ("sgt", "pivotcvae_sgt_pi")])
+def test_pivot_forward(golden, name, train, key):
+    fx = golden(name)
+    m = build_pivot(fx, key)
+    cfg = fx.cfg
+    tag = "fwd_%s/" % train
+    m.noise.push("eps", T(fx[tag + "eps"]))
+    if (tag + "noise") in fx:
+        m.noise.push("race", T(fx[tag + "noise"]))
+    with torch.no_grad():
+        p, rx, z, emb, mu, lv = m.forward(T(fx["in/slates"]), T(fx["in/resp"]), u=_users(fx))
+    assert p.shape == (cfg["B"] * cfg["L"], cfg["n_items"])
+    np.testing.assert_allclose(N(mu), fx[tag + "z_mu"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(N(lv), fx[tag + "z_logvar"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(N(z), fx[tag + "z"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N(rx), fx[tag + "rx"], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(N(emb), fx[tag + "emb"])
+    n = fx[tag + "p_rows"].shape[0]
+    np.testing.assert_allclose(N(p[:n]), fx[tag + "p_rows"], rtol=1e-4, atol=1e-5)   # logits within 1e-4
+
+
+@pytest.mark.parametrize("name", ["pivot_small", "pivot_small_nouser"])
+@pytest.mark.parametrize("ntag", ["mask", "full"])
+def test_gen_loss_and_grads(golden, name, ntag):
+    """get_gen_loss (train_generative.py:44-65) + backward vs torch autograd of the reference."""
+    from pivotcvae_b200.train_generative import get_gen_loss
+    fx = golden(name)
+    m = build_pivot(fx)
+    t2 = "loss_gt_%s/" % ntag
+    m.noise.push("eps", T(fx[t2 + "eps"]))
+    m.noise.push("mask", T(fx[t2 + "bitmask"].view(np.int32)))
+    batch = {"slates": fx["in/slates"], "users": fx["in/users"].reshape(-1, 1), "responses": fx["in/resp"].astype(np.float64)}
+    loss, rec, kld = get_gen_loss(batch, m, None, 0.01, n_neg=int(fx[t2 + "n_neg"]))
+    want = fx[t2 + "loss"]
+    np.testing.assert_allclose([loss.item(), rec.item(), kld.item()], want, rtol=1e-4)
+    loss.backward()
+    grads = fx.sub(t2 + "grad/")
+    assert grads
+    for pname, prm in m.named_parameters():
+        if pname in grads:
+            np.testing.assert_allclose(N(prm.grad), grads[pname], rtol=2e-3, atol=2e-6, err_msg=pname)
+        else:
+            assert prm.grad is None, pname      # PSM and the frozen tables get no gradient
+
+
+@pytest.mark.parametrize("name", ["list_small", "list_small_user"])
+def test_list_gen_loss_and_grads(golden, name):
+    from pivotcvae_b200.train_generative import get_gen_loss
+    fx = golden(name)
+    m = build_list(fx)
+    for ntag in ("mask", "full"):
+        t2 = "loss_%s/" % ntag
+        m.zero_grad()
+        m.noise.push("eps", T(fx[t2 + "eps"]))
+        m.noise.push("mask", T(fx[t2 + "bitmask"].view(np.int32)))
+        batch = {"slates": fx["in/slates"], "users": fx["in/users"].reshape(-1, 1), "responses": fx["in/resp"]}
+        loss, rec, kld = get_gen_loss(batch, m, None, 0.01, n_neg=int(fx[t2 + "n_neg"]))
+        np.testing.assert_allclose([loss.item(), rec.item(), kld.item()], fx[t2 + "loss"], rtol=1e-4)
+        loss.backward()
+        for pname, prm in m.named_parameters():
+            g = fx.sub(t2 + "grad/").get(pname)
+            if g is not None:
+                np.testing.assert_allclose(N(prm.grad), g, rtol=2e-3, atol=2e-6, err_msg=pname)
+
+
+def test_response_mlp_and_env_on_slates(golden):
+    from pivotcvae_b200.env.response_model import UserResponseModel_MLP
+    fx = golden("env_small")
+    n_items, n_users, L, D, B = [int(v) for v in fx["cfg"]]
+    for tag, nu in (("mlp_user/", False), ("mlp_nouser/", True)):
+        e = UserResponseModel_MLP(n_items - 1, n_users - 1, D, L, [(L + (0 if nu else 1)) * D, 64, 48, L], "cuda:0", nu)
+        e.load_state_dict({k: torch.from_numpy(v) for k, v in fx.sub(tag + "sd/").items()})
+        e.to("cuda:0")
+        out = e(T(fx["in/slates"]), T(fx["in/users"]))
+        np.testing.assert_allclose(N(out), fx[tag + "out"], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(N(out), oracle.resp_mlp(fx.sub(tag + "sd/"), fx["in/slates"], fx["in/users"], nu))
+
+
+def test_urm_classes(golden):
+    from pivotcvae_b200.env.response_model import URM, URM_P, URM_P_MR
+    fx = golden("env_small")
+    n_items, n_users, L, D, B = [int(v) for v in fx["cfg"]]
+    ctors = {"urm": lambda: URM(n_items - 1, n_users - 1, L, D, "cpu", False),
+             "urm_p": lambda: URM_P(n_items - 1, n_users - 1, L, D, "cpu", False, 0.3, -0.1),
+             "urm_p_mr": lambda: URM_P_MR(n_items - 1, n_users - 1, L, D, "cpu", False, 0.3, -0.1, 0.7)}
+    for name, ctor in ctors.items():
+        e = ctor()
+        e.load_state_dict({k: torch.from_numpy(v) for k, v in fx.sub(name + "/sd/").items()})
+        if hasattr(e, "posBias"):
+            e.posBias = torch.from_numpy(fx[name + "/posBias"])
+            e.posDependentBias = torch.from_numpy(fx[name + "/posDependentBias"])
+        e = e.to("cuda:0")
+        assert e.device == "cuda:0"
+        out = e(T(fx["in/slates"]), T(fx["in/users"]))
+        np.testing.assert_allclose(N(out), fx[name + "/out"], rtol=1e-5, atol=1e-6)
+        p, dEmb, dBias, uEmb, uBias = e.core_forward(T(fx["in/slates"]), T(fx["in/users"]))
+        assert dEmb.shape == (B, L, D) and torch.equal(p, out)
+
+
+def test_eval_loop_and_pickle(golden, tmp_path):
+    """The 100x5 recommendation test shape (train_generative.py:168-195) and whole-model pickling (:199)."""
+    from pivotcvae_b200.env.response_model import UserResponseModel_MLP
+    from pivotcvae_b200.train_generative import recommendation_test
+    fx = golden("pivot_small")
+    cfg = fx.cfg
+    m = build_pivot(fx)
+    env = UserResponseModel_MLP(cfg["n_items"] - 1, cfg["n_users"] - 1, cfg["D"], cfg["L"],
+                                [(cfg["L"] + 1) * cfg["D"], cfg["hidden"], cfg["hidden"], cfg["L"]], "cuda:0", False)
+    env.load_state_dict({k: torch.from_numpy(v) for k, v in fx.sub("env_sd/").items()})
+    env.to("cuda:0")
+    items = T(fx["rec_pi_k1/items"]).view(cfg["B"], -1)
+    np.testing.assert_allclose(N(env(items, T(fx["in/users"]))), fx["env/resp"], rtol=1e-4, atol=1e-5)
+    mn, me, mx = recommendation_test(m, env, 32, n_trial=3, n_context=5)
+    assert mn.shape == (5,) and bool((mn <= me).all()) and bool((me <= mx).all())
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    tag = "rec_pi_k1/"
+    m2.noise.push("eps", T(fx[tag + "eps"]))
+    it2, _ = m2.recommend(T(fx[tag + "ctx"]), T(fx["in/users"]), return_item=True)
+    assert np.array_equal(N(it2), fx[tag + "items"])
+
+
+def test_no_cpu_fallback(golden):
+    import pivotcvae_b200._lib as L
+    from pivotcvae_b200.models.pivotcvae import UserPivotCVAE
+    fx = golden("pivot_small")
+    with pytest.raises(L.PcvError):
+        from gpu_util import _Emb
+        sd = fx.sub("sd/")
+        UserPivotCVAE(_Emb(sd["docEmbed.weight"]), _Emb(sd["userEmbed.weight"]), 5, 8, 16, 6, list(fx["cfg/enc"]),
+                      list(fx["cfg/psm"]), list(fx["cfg/scm"]), list(fx["cfg/prior"]), False, "cpu")
