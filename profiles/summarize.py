@@ -1,0 +1,58 @@
+"""Summarise ncu artefacts brought back in gpurun_out/ into text files under profiles/.
+
+    python profiles/summarize.py launches gpurun_out/launches_r1.csv > profiles/r1_launches.txt
+    python profiles/summarize.py full gpurun_out/prof_ss_simt.ncu-rep > profiles/r1_ss_simt_full.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_elapsed.max",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+        "smsp__warp_issue_stalled_not_selected_per_warp_active.pct"]
+
+
+def launches(path):
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        k = row["Kernel Name"][:90]
+        v = float(row["Metric Value"].replace(",", ""))
+        a = agg.setdefault(k, [0, 0.0, row["Metric Unit"]])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print("# per-kernel totals from %s (ncu gpu__time_duration.sum, cold-cache, serialised: compare SHARES)" % path)
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print("%-92s n=%4d total=%12.1f %s avg=%10.1f share=%5.1f%%" % (k, a[0], a[1], a[2], a[1] / a[0], 100 * a[1] / tot))
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(out.splitlines()))
+    hdr, units = r[0], r[1]
+    idx = [hdr.index(w) for w in WANT if w in hdr]
+    print("# selected metrics from %s (ncu --set full --clock-control none)" % path)
+    for row in r[2:]:
+        for i in idx:
+            print("  %s = %s %s" % (hdr[i], row[i], units[i]))
+        print("  --")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
