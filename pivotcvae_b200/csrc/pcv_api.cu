@@ -42,6 +42,18 @@ __global__ void normalize_rows_kernel(const float *__restrict__ W, int64_t n, in
   for (int k = 0; k < dim; ++k) out[i * dim + k] = w[k] / nrm;
 }
 
+// max_j |w_j|_2^2 as an ordered-uint atomicMax (norms are >= 0)
+__global__ void max_row_norm2_kernel(const float *__restrict__ W, int64_t n, int dim, unsigned int *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float ss = 0.f;
+  if (i < n)
+    for (int k = 0; k < dim; ++k) ss = fmaf(W[i * dim + k], W[i * dim + k], ss);
+  ss = warp_max(ss);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(ss));
+}
+
+int table_init_tc(Table *t);  // score_select_tc.cu
+
 }  // namespace pcv
 
 using namespace pcv;
@@ -87,6 +99,29 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
   t->tmap_valid = 0;
   cudaGetDevice(&t->device);
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, t->device);
+  // one-off: max row norm (error bound of the tf32 filter) + TMA descriptor
+  {
+    unsigned int *d_max = nullptr;
+    unsigned int h_max = 0;
+    cudaError_t e = cudaDeviceSynchronize();  // the table may still be being written on another stream
+    if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(d_max, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) {
+      max_row_norm2_kernel<<<(unsigned)((n_rows + 255) / 256), 256>>>(W, n_rows, dim, d_max);
+      count_launch();
+      e = cudaMemcpy(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost);
+    }
+    if (d_max) cudaFree(d_max);
+    if (e != cudaSuccess) {
+      set_error("pcv_table_create: %s", cudaGetErrorString(e));
+      delete t;
+      return PCV_ERR_CUDA;
+    }
+    float m2;
+    memcpy(&m2, &h_max, sizeof(float));
+    t->max_row_norm = sqrtf(m2) * 1.000001f;
+  }
+  table_init_tc(t);
   *out = reinterpret_cast<pcv_table *>(t);
   return PCV_OK;
 }

@@ -25,6 +25,7 @@ struct Table {
   // tcgen05 path: 128-byte CUtensorMap over W (filled lazily; valid=0 if unavailable)
   alignas(64) unsigned char tmap[128];
   int tmap_valid;
+  float max_row_norm;  // max_j |w_j|_2 (error bound of the tf32 filter)
 };
 
 #define PCV_CHECK_ARG(cond, msg)                              \

@@ -330,6 +330,13 @@ static int dispatch_dim(const Table *t, const SSPlan &p, const float *Q, int64_t
   return PCV_ERR_UNSUPPORTED;
 }
 
+void launch_select_finalize(const float *pv, const int32_t *pi, int n_parts, int64_t M, int64_t row_offset,
+                            int64_t *out_idx, float *out_val, cudaStream_t st) {
+  const int threads = 256;
+  select_finalize_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(pv, pi, n_parts, M, row_offset,
+                                                                                       out_idx, out_val);
+}
+
 // tcgen05 engine (score_select_tc.cu)
 int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val,
                     void *ws, size_t ws_bytes, cudaStream_t st);
@@ -372,9 +379,12 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
   cudaStream_t st = (cudaStream_t)stream;
 
   int engine = opts->engine;
-  if (opts->mode == PCV_SELECT_GREEDY && engine == PCV_ENGINE_TCGEN05) {
-    if (!score_select_tc_supported(t)) {
-      set_error("score_select: tcgen05 engine unsupported for dim %d", t->dim);
+  if (engine == PCV_ENGINE_AUTO)  // tensor cores whenever the shape allows and the catalog is not tiny
+    engine = (opts->mode == PCV_SELECT_GREEDY && score_select_tc_supported(t) && t->n_rows >= 2048)
+                 ? PCV_ENGINE_TCGEN05 : PCV_ENGINE_SIMT;
+  if (engine == PCV_ENGINE_TCGEN05) {
+    if (opts->mode != PCV_SELECT_GREEDY || !score_select_tc_supported(t)) {
+      set_error("score_select: tcgen05 engine needs greedy mode and dim 8 (dim %d, mode %d)", t->dim, opts->mode);
       return PCV_ERR_UNSUPPORTED;
     }
     return score_select_tc(t, Q, M, out_idx, out_val, workspace, workspace_bytes, st);
