@@ -15,10 +15,11 @@
 // Arithmetic contract: y[n] = (fma-chain over k ascending of x[k]*W[n][k], from 0) + b[n],
 // i.e. the K loop is never split, so results are bit-identical to the CPU oracle.
 //
-// Layout: a CTA owns BM batch rows; activations ping-pong between two shared
-// memory buffers [BM][ld]; each layer's weights stream through a [16][256]
-// shared-memory stage (transposed on the fly from nn.Linear's [n_out][n_in]);
-// a thread accumulates a (BM/8) x 8 register tile.
+// Layout: a CTA owns BM = 8/16/32 batch rows; activations ping-pong between two
+// transposed shared-memory buffers actT[k][row]; each layer's weights stream through
+// a double-buffered [16][256] shared-memory stage (transposed on the fly from
+// nn.Linear's [n_out][n_in], prefetched one chunk ahead in registers); a thread
+// accumulates an 8-row x CT-column register tile.
 #include "pcv_common.cuh"
 
 namespace pcv {
@@ -56,150 +57,186 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t offset, int64_t 
   n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
 }
 
-template <int BM>
+// Thread mapping: 256 threads = (256/CT column groups) x (CT row groups of 8 rows);
+// a thread owns CT adjacent output columns x 8 batch rows, BM = 8*CT rows per CTA.
+// Activations live TRANSPOSED in shared memory (actT[k][row]) so a thread's 8 rows
+// are two broadcast LDS.128; the weight stage wst[kk][n] is read conflict-free.
+// Weight chunks are prefetched into registers one chunk ahead (across column blocks
+// and layers) and double-buffered in shared memory: one __syncthreads per chunk.
+template <int CT>
 __global__ void __launch_bounds__(MLP_THREADS)
 mlp_fwd_kernel(const MlpParams P, int64_t B) {
-  constexpr int RT = BM / 8;  // rows per thread (warp w owns rows w*RT .. w*RT+RT-1)
+  constexpr int BM = 8 * CT;
+  constexpr int CG = MLP_NB / CT;   // column groups (threads along n)
+  constexpr int ALD = BM + 4;       // actT row stride (floats)
   extern __shared__ __align__(16) float smem[];
-  const int ld = P.ld;
-  float *actA = smem;
-  float *actB = actA + BM * ld;
-  float *wst = actB + BM * ld;  // [MLP_KC][MLP_WLD]
+  const int ld = P.ld;              // max width (multiple of 4)
+  float *actA = smem;               // [ld][ALD]
+  float *actB = actA + ld * ALD;
+  float *wst = actB + ld * ALD;     // [2][MLP_KC][MLP_WLD]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rg = tid / CG;
   const int64_t b0 = (int64_t)blockIdx.x * BM;
   const pcv_mlp_desc &d = P.d;
 
-  // ---------------- prologue: assemble x0 into actA ----------------
+  // ---------------- weight-chunk stream (layer, column block, k-chunk) ----------------
+  int pl = 0, pnb = 0, pkc = 0;     // position of the chunk held in wv
+  float wv[MLP_KC];
+  auto fetch = [&](int l, int nb, int kc) {
+    const int K = d.layer[l].n_in, NO = d.layer[l].n_out;
+    const int n = nb + tid;
+    if (n < NO) {
+      const float *wrow = d.layer[l].W + (int64_t)n * K + kc;
+      if (kc + MLP_KC <= K && ((K & 3) == 0)) {
+#pragma unroll
+        for (int v = 0; v < MLP_KC / 4; ++v) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4 *>(wrow) + v);
+          wv[4 * v] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = (kc + kk < K) ? __ldg(wrow + kk) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = 0.f;
+    }
+  };
+  auto advance = [&]() {  // -> false when the stream is exhausted
+    pkc += MLP_KC;
+    if (pkc >= d.layer[pl].n_in) {
+      pkc = 0;
+      pnb += MLP_NB;
+      if (pnb >= d.layer[pl].n_out) { pnb = 0; ++pl; }
+    }
+    return pl < d.n_layers;
+  };
+  fetch(0, 0, 0);  // in flight during the prologue
+
+  // ---------------- prologue: assemble x0 into actA (transposed) ----------------
   {
     constexpr int TPR = MLP_THREADS / BM;  // threads per row
     const int row = tid / TPR, sub = tid % TPR;
     const int64_t b = b0 + row;
-    float *x = actA + row * ld;
+    float *x = actA + row;                 // element e at x[e * ALD]
     if (b < B) {
       for (int s = 0; s < d.n_segments; ++s) {
         const pcv_segment &sg = d.seg[s];
-        float *xs = x + P.seg_off[s];
+        float *xs = x + P.seg_off[s] * ALD;
         if (sg.kind == PCV_SEG_DENSE) {
           const float *src = (const float *)sg.ptr + b * sg.width;
-          for (int e = sub; e < sg.width; e += TPR) xs[e] = src[e];
+          for (int e = sub; e < sg.width; e += TPR) xs[e * ALD] = src[e];
         } else if (sg.kind == PCV_SEG_ONEHOT) {
           const float *r = (const float *)sg.ptr + b * sg.count;
           float sum = 0.f;
           for (int l = 0; l < sg.count; ++l) sum += r[l];
           const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
-          for (int e = sub; e <= sg.count; e += TPR) xs[e] = (e == hot) ? 1.f : 0.f;
+          for (int e = sub; e <= sg.count; e += TPR) xs[e * ALD] = (e == hot) ? 1.f : 0.f;
         } else {  // GATHER
           const float *tab = (const float *)sg.ptr;
           const int n = sg.count * sg.width;
           for (int e = sub; e < n; e += TPR) {
             const int c = e / sg.width, k = e - c * sg.width;
-            xs[e] = tab[sg.idx[b * sg.count + c] * (int64_t)sg.width + k];
+            xs[e * ALD] = tab[sg.idx[b * sg.count + c] * (int64_t)sg.width + k];
           }
         }
       }
     } else {
-      for (int e = sub; e < P.n_in0; e += TPR) x[e] = 0.f;
+      for (int e = sub; e < P.n_in0; e += TPR) x[e * ALD] = 0.f;
     }
     __syncthreads();
     // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order
     for (int s = 0; s < d.n_segments; ++s) {
       if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
       const int w = P.seg_off[s + 1] - P.seg_off[s];
-      float *xs = x + P.seg_off[s];
+      float *xs = x + P.seg_off[s] * ALD;
       float ss = 0.f;
-      for (int e = 0; e < w; ++e) ss = fmaf(xs[e], xs[e], ss);  // every thread of the row: same value
+      for (int e = 0; e < w; ++e) ss = fmaf(xs[e * ALD], xs[e * ALD], ss);  // every thread of the row: same value
       const float nrm = fmaxf(sqrtf(ss), 1e-12f);
       __syncthreads();
-      for (int e = sub; e < w; e += TPR) xs[e] = xs[e] / nrm;
+      for (int e = sub; e < w; e += TPR) xs[e * ALD] = xs[e * ALD] / nrm;
       __syncthreads();
     }
     if (b < B) {
       if (d.x0) {
         float *dst = d.x0 + b * P.n_in0;
-        for (int e = sub; e < P.n_in0; e += TPR) dst[e] = x[e];
+        for (int e = sub; e < P.n_in0; e += TPR) dst[e] = x[e * ALD];
       }
       if (d.copy_seg >= 0) {
         const int w = P.seg_off[d.copy_seg + 1] - P.seg_off[d.copy_seg];
-        const float *xs = x + P.seg_off[d.copy_seg];
+        const float *xs = x + P.seg_off[d.copy_seg] * ALD;
         float *dst = d.out + b * d.out_ld;
-        for (int e = sub; e < w; e += TPR) dst[e] = xs[e];
+        for (int e = sub; e < w; e += TPR) dst[e] = xs[e * ALD];
       }
     }
   }
 
   // ---------------- layers ----------------
   float *cur = actA, *nxt = actB;
+  int buf = 0;
+  bool more = true;
   for (int l = 0; l < d.n_layers; ++l) {
     const pcv_linear L = d.layer[l];
     const bool last = (l == d.n_layers - 1);
     const int K = L.n_in;
     for (int nb = 0; nb < L.n_out; nb += MLP_NB) {
-      float acc[RT][8];
+      float acc[8][CT];
 #pragma unroll
-      for (int r = 0; r < RT; ++r)
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
 
       for (int kc = 0; kc < K; kc += MLP_KC) {
-        __syncthreads();  // previous chunk consumed (and cur fully written)
-        {
-          // stage W[nb + n][kc .. kc+15] -> wst[kk][n]; thread n = tid
-          const int n = nb + tid;
-          float wv[MLP_KC];
-          if (n < L.n_out) {
-            const float *wrow = L.W + (int64_t)n * K + kc;
-            if (kc + MLP_KC <= K && ((K & 3) == 0)) {
+        float *ws = wst + buf * (MLP_KC * MLP_WLD);
 #pragma unroll
-              for (int v = 0; v < MLP_KC / 4; ++v) {
-                float4 t4 = __ldg(reinterpret_cast<const float4 *>(wrow) + v);
-                wv[4 * v] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
-              }
-            } else {
-#pragma unroll
-              for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = (kc + kk < K) ? __ldg(wrow + kk) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = 0.f;
-          }
-#pragma unroll
-          for (int kk = 0; kk < MLP_KC; ++kk) wst[kk * MLP_WLD + tid] = wv[kk];
-        }
+        for (int kk = 0; kk < MLP_KC; ++kk) ws[kk * MLP_WLD + tid] = wv[kk];
         __syncthreads();
-        const int kmax = min(MLP_KC, K - kc);
-        for (int kk = 0; kk < kmax; ++kk) {
-          const float4 w0 = *reinterpret_cast<const float4 *>(wst + kk * MLP_WLD + lane * 4);
-          const float4 w1 = *reinterpret_cast<const float4 *>(wst + kk * MLP_WLD + 128 + lane * 4);
-#pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            const float a = cur[(warp * RT + r) * ld + kc + kk];
-            acc[r][0] = fmaf(a, w0.x, acc[r][0]);
-            acc[r][1] = fmaf(a, w0.y, acc[r][1]);
-            acc[r][2] = fmaf(a, w0.z, acc[r][2]);
-            acc[r][3] = fmaf(a, w0.w, acc[r][3]);
-            acc[r][4] = fmaf(a, w1.x, acc[r][4]);
-            acc[r][5] = fmaf(a, w1.y, acc[r][5]);
-            acc[r][6] = fmaf(a, w1.z, acc[r][6]);
-            acc[r][7] = fmaf(a, w1.w, acc[r][7]);
-          }
+        if (more) {
+          more = advance();
+          if (more) fetch(pl, pnb, pkc);   // next chunk's loads fly during this chunk's FMAs
         }
+        const int kmax = min(MLP_KC, K - kc);
+        const float *ap = cur + (size_t)kc * ALD + rg * 8;
+        for (int kk = 0; kk < kmax; ++kk) {
+          const float4 a0 = *reinterpret_cast<const float4 *>(ap + kk * ALD);
+          const float4 a1 = *reinterpret_cast<const float4 *>(ap + kk * ALD + 4);
+          float w[CT];
+          if (CT == 4) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(ws + kk * MLP_WLD + cg * 4);
+            w[0] = t4.x; w[1 % CT] = t4.y; w[2 % CT] = t4.z; w[3 % CT] = t4.w;
+          } else if (CT == 2) {
+            const float2 t2 = *reinterpret_cast<const float2 *>(ws + kk * MLP_WLD + cg * 2);
+            w[0] = t2.x; w[1 % CT] = t2.y;
+          } else {
+            w[0] = ws[kk * MLP_WLD + cg];
+          }
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
+        }
+        buf ^= 1;
       }
       // epilogue of this column block: bias + activation -> nxt (+ HBM)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int n = nb + (c < 4 ? lane * 4 + c : 128 + lane * 4 + (c - 4));
+      for (int c = 0; c < CT; ++c) {
+        const int n = nb + cg * CT + c;
         if (n < L.n_out) {
           const float bias = __ldg(L.b + n);
+          float v[8];
 #pragma unroll
-          for (int r = 0; r < RT; ++r) {
-            const int row = warp * RT + r;
-            const float v = apply_act(acc[r][c] + bias, L.act);
-            nxt[row * ld + n] = v;
-            const int64_t b = b0 + row;
+          for (int r = 0; r < 8; ++r) v[r] = apply_act(acc[r][c] + bias, L.act);
+          float *np = nxt + (size_t)n * ALD + rg * 8;
+          *reinterpret_cast<float4 *>(np) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4 *>(np + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int64_t b = b0 + rg * 8 + r;
             if (b < B) {
-              if (last) d.out[b * d.out_ld + d.out_col0 + n] = v;
-              else if (d.acts[l]) d.acts[l][b * L.n_out + n] = v;
+              if (last) d.out[b * d.out_ld + d.out_col0 + n] = v[r];
+              else if (d.acts[l]) d.acts[l][b * L.n_out + n] = v[r];
             }
           }
         }
@@ -216,8 +253,8 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
       const int row = e / Z, j = e - row * Z;
       const int64_t b = b0 + row;
       if (b >= B) continue;
-      const float mu = cur[row * ld + j];
-      const float lv = cur[row * ld + Z + j];
+      const float mu = cur[j * ALD + row];
+      const float lv = cur[(Z + j) * ALD + row];
       float eps;
       if (d.eps) {
         eps = d.eps[b * Z + j];
@@ -320,22 +357,26 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
   int rc = check_arch();
   if (rc != PCV_OK) return rc;
 
-  P.ld = ((maxw + 3) & ~3) + 4;
+  P.ld = (maxw + 3) & ~3;
   int sm_count = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  const bool small = B <= (int64_t)sm_count * 32;
-  const int BM = small ? 16 : 32;
-  size_t smem = (size_t)(2 * BM * P.ld + MLP_KC * MLP_WLD) * sizeof(float);
+  // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs
+  const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
+  const int BM = 8 * CT;
+  size_t smem = (size_t)(2 * P.ld * (BM + 4) + 2 * MLP_KC * MLP_WLD) * sizeof(float);
   int64_t blocks = (B + BM - 1) / BM;
   cudaStream_t st = (cudaStream_t)stream;
-  if (small) {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<16><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+  if (CT == 1) {
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<1><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+  } else if (CT == 2) {
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<2><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
   } else {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<32><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<4><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
   }
   PCV_LAUNCH_CHECK();
   return PCV_OK;

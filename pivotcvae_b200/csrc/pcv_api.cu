@@ -53,6 +53,7 @@ __global__ void max_row_norm2_kernel(const float *__restrict__ W, int64_t n, int
 }
 
 int table_init_tc(Table *t);  // score_select_tc.cu
+void table_free_tc(Table *t);
 
 }  // namespace pcv
 
@@ -97,6 +98,7 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
   t->dim = dim;
   t->row_offset = row_offset;
   t->tmap_valid = 0;
+  t->packed = nullptr;
   cudaGetDevice(&t->device);
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, t->device);
   // one-off: max row norm (error bound of the tf32 filter) + TMA descriptor
@@ -126,7 +128,12 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
   return PCV_OK;
 }
 
-void pcv_table_destroy(pcv_table *t) { delete reinterpret_cast<Table *>(t); }
+void pcv_table_destroy(pcv_table *th) {
+  Table *t = reinterpret_cast<Table *>(th);
+  if (!t) return;
+  table_free_tc(t);
+  delete t;
+}
 
 int pcv_normalize_rows(const float *W, int64_t n_rows, int dim, float *out,
                        pcv_stream_t stream) {

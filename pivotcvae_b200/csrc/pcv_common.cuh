@@ -22,9 +22,9 @@ struct Table {
   int64_t row_offset;
   int device;
   int sm_count;
-  // tcgen05 path: 128-byte CUtensorMap over W (filled lazily; valid=0 if unavailable)
-  alignas(64) unsigned char tmap[128];
-  int tmap_valid;
+  // tcgen05 path: pre-swizzled (SWIZZLE_32B image) copy of W owned by the handle
+  float *packed;
+  int tmap_valid;  // 1 when the tcgen05 engine can serve this table
   float max_row_norm;  // max_j |w_j|_2 (error bound of the tf32 filter)
 };
 

@@ -4,27 +4,31 @@
 // arg-max of the fp32 sequential-k FMA chain, ties -> lowest index.  The tensor
 // cores only FILTER:
 //
-//   1. TMA (cp.async.bulk.tensor, SWIZZLE_32B) streams 256-item table tiles
-//      ([item][8 x fp32] = 32 B rows, K-major) into a 4-stage shared-memory ring.
+//   1. The table handle keeps a PRE-SWIZZLED copy of the frozen table (rows with bit 2
+//      of the row index set have their two 16-byte halves swapped = the K-major
+//      SWIZZLE_32B shared-memory image).  One TMA bulk copy (cp.async.bulk, 8 KB,
+//      a single contiguous request) per 256-item tile streams it into a 16-stage
+//      shared-memory ring.  (A 2-D tensor-map load with a 32-byte inner box was
+//      measured ~8x slower: one 32 B request per row; see profiles/.)
 //   2. One elected thread issues tcgen05.mma.kind::tf32, M=128 (query rows, staged
 //      once per CTA), N=256, K=8 per tile; accumulators ping-pong between two
 //      256-column TMEM buffers (512 columns = all of TMEM).
-//   3. Eight epilogue warps read their TMEM lanes (tcgen05.ld 32x32b.x32: thread =
+//   3. TC_EPI_WARPS epilogue warps read their TMEM lanes (tcgen05.ld 32x32b.x32: thread =
 //      query row), keep a running max r of the APPROXIMATE scores and record every
-//      item whose approximate score >= r - band in a per-row shared-memory list.
+//      32-item chunk whose approximate maximum is >= r - band in a per-row
+//      shared-memory list (fast path: 16 FMNMX3 + 1 compare per 32 logits).
 //      band = 2*eps, eps = 1.25 * 2^-9 * |q|_2 * max_j |w_j|_2 bounds |tf32 - fp32 chain|
 //      (both operands truncated to 10 mantissa bits: relative 2^-10 each), so the
 //      exact arg-max (and every exact tie) is always in the list.
-//   4. Whenever a list fills up, and at the end, the thread COLLAPSES it: it
-//      re-scores the listed items with the exact fp32 FMA chain from the fp32
-//      table and keeps the exact winner (ties -> lowest index) in registers.
-//      The shared finalize kernel merges the per-split winners.
+//   4. Each (row, split, column-slice) stream hands its running max and its (<= 4)
+//      surviving chunks to tc_refine_kernel: one warp per row takes R = max over the
+//      streams, and re-scores item-by-item (lane = item, coalesced 1 KB reads) every
+//      chunk still inside the band of R with the exact fp32 FMA chain from the fp32
+//      table; winner = largest exact score, ties -> lowest index.
 //
 // The (M x N) logits never leave TMEM, and the result is exact for any input
-// (duplicated rows and exact ties just collapse more often).
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
+// (streams with more chunks inside the band than the lists hold — heavy exact
+// ties — are flagged and scanned exactly by the refine kernel).
 #include "pcv_common.cuh"
 
 namespace pcv {
@@ -32,16 +36,19 @@ namespace pcv {
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
 constexpr int TC_D = 8;
-constexpr int TC_STAGES = 4;
-constexpr int TC_CAP = 16;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_STAGES = 16;  // 8 KB tiles: ~16 in flight to cover the L2/HBM latency (Little)
+constexpr int TC_EPI_WARPS = 8;                      // multiple of 4 (each warp reads one TMEM lane quarter)
+constexpr int TC_SLICES = TC_EPI_WARPS / 4;          // column slices of a 256-column tile
+constexpr int TC_SW = TC_BN / TC_SLICES;             // columns per slice
+constexpr int TC_CAP = 32 / TC_SLICES;               // in-kernel recorded-chunk list capacity per (slice, row)
+constexpr int TC_OUT = 8;                            // recorded chunks handed to the refine kernel per (stream, row)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp0 TMA, warp1 MMA/TMEM, 8 epilogue warps
 constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 4;
 
 struct __align__(1024) TcSmem {
   float b[TC_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
   float a[TC_BM * TC_D];                       // query tile, same layout
-  int32_t cand[2][TC_CAP][TC_BM];              // candidate item indices per (column half, row)
+  unsigned long long cand[TC_SLICES][TC_CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
   unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
@@ -70,10 +77,10 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
       "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+// TMA bulk copy global -> shared (contiguous bytes), completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, uint32_t bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // K-major, SWIZZLE_32B shared-memory matrix descriptor: rows of 32 B, 8-row groups 256 B apart.
@@ -128,20 +135,23 @@ __device__ __forceinline__ void umma_commit(void *bar) {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
-  float m[11];
+// max of 32 accumulator values; g[0..10] are the maxima of the 3-element groups
+// (g[10] covers elements 30, 31) so the rare slow path can skip whole groups.
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[11]) {
 #pragma unroll
   for (int i = 0; i < 10; ++i)
-    m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-  m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-  float a = max3(m[0], m[1], m[2]), b = max3(m[3], m[4], m[5]), c = max3(m[6], m[7], m[8]);
-  return max3(max3(a, b, c), m[9], m[10]);
+    g[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  g[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  float a = max3(g[0], g[1], g[2]), b = max3(g[3], g[4], g[5]), c = max3(g[6], g[7], g[8]);
+  return max3(max3(a, b, c), g[9], g[10]);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-score_select_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const float *__restrict__ W, int64_t n_rows,
+score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
                        const float *__restrict__ Q, int64_t M, int64_t items_per_split, float band_scale,
-                       float *__restrict__ part_val, int32_t *__restrict__ part_idx) {
+                       float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
+                       unsigned long long *__restrict__ out_ent, unsigned int *__restrict__ ovf_count,
+                       unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cap) {
   extern __shared__ unsigned char smem_raw[];
   TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -186,8 +196,10 @@ score_select_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const float *_
         const int s = t % TC_STAGES;
         const uint32_t ph = (t / TC_STAGES) & 1;
         mbar_wait(&S.empty[s], ph ^ 1);
-        mbar_expect_tx(&S.full[s], TC_TILE_BYTES);
-        tma_load_2d(S.b[s], &tmapW, 0, (int)(j_begin + (int64_t)t * TC_BN), &S.full[s]);
+        const int64_t j0 = j_begin + (int64_t)t * TC_BN;
+        const uint32_t bytes = (uint32_t)min((int64_t)TC_TILE_BYTES, (n_rows - j0) * (int64_t)(TC_D * 4));
+        mbar_expect_tx(&S.full[s], bytes);  // rows past the end of the table keep stale data: masked below
+        tma_bulk_load(S.b[s], Wsw + j0 * TC_D, bytes, &S.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -209,7 +221,7 @@ score_select_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const float *_
   } else {
     // ---------------- epilogue: thread = (query row, column half) ----------------
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;         // which 128 columns of every 256-column tile
+    const int slice = (warp - 2) >> 2;        // which TC_SW columns of every 256-column tile
     const int trow = quarter * 32 + lane;
     const int64_t row = row_base + trow;
     const bool live = row < M;
@@ -226,72 +238,106 @@ score_select_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const float *_
 #pragma unroll
     for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
     const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
-    float r = live ? -INFINITY : INFINITY;   // dummy rows never record anything
+    // running max of the approximate scores; finite start so that masked (-inf) columns
+    // never pass, +inf for dummy rows so that nothing ever passes
+    float r = live ? -3.0e38f : INFINITY;
     float thr = r;
     int cnt = 0;
-    float best = -INFINITY;                   // exact winner so far
-    int32_t bidx = 0x7fffffff;
-    int32_t *list = &S.cand[half][0][trow];   // entry e at list[e * TC_BM]
+    unsigned long long *list = &S.cand[slice][0][trow];  // entry e at list[e * TC_BM]
 
-    // exact fp32 re-score of the listed candidates (sequential-k FMA chain)
-    auto collapse = [&]() {
+    bool ovf = false;
+    // rare: more chunks inside the band than a list holds -> append them to the global overflow
+    // buffer (exactly re-scored by tc_overflow_kernel); only if that is full too is the stream flagged
+    auto spill = [&](unsigned long long ent) {
+      const unsigned int pos = atomicAdd(ovf_count, 1u);
+      if (pos < ovf_cap) { ovf_ent[pos] = ent; ovf_row[pos] = (int32_t)row; }
+      else ovf = true;
+    };
+    // a full list is compacted in place: chunks whose approximate maximum fell out of the
+    // band of the (grown) running max can never hold the winner
+    auto compact = [&]() {
+      int k = 0;
       for (int e = 0; e < cnt; ++e) {
-        const int32_t j = list[e * TC_BM];
-        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)j * TC_D));
-        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + (int64_t)j * TC_D) + 1);
-        float s = 0.f;
-        s = fmaf(q[0], w0.x, s); s = fmaf(q[1], w0.y, s); s = fmaf(q[2], w0.z, s); s = fmaf(q[3], w0.w, s);
-        s = fmaf(q[4], w1.x, s); s = fmaf(q[5], w1.y, s); s = fmaf(q[6], w1.z, s); s = fmaf(q[7], w1.w, s);
-        if (s > best || (s == best && j < bidx)) { best = s; bidx = j; }
+        const unsigned long long ent = list[e * TC_BM];
+        if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) list[(k++) * TC_BM] = ent;
       }
-      cnt = 0;
+      cnt = k;
     };
 
+    // one 32-column chunk: 16 FMNMX3 + one compare; a chunk whose approximate maximum is
+    // inside the band of the running max is only RECORDED (one shared-memory store) — the
+    // exact fp32 re-score happens in the refine kernel
+    auto process = [&](uint32_t (&v)[32], int32_t jb) {
+      float g[11];
+      const float m = chunk_max(v, g);
+      if (m >= thr) {
+        r = fmaxf(r, m);
+        thr = r - band;
+        if (cnt == TC_CAP) compact();
+        if (cnt < TC_CAP) {
+          list[cnt * TC_BM] = ((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb;
+          ++cnt;
+        } else {
+          spill(((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb);
+        }
+      }
+    };
+    auto mask_tail = [&](uint32_t (&v)[32], int col0, int n_valid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i >= n_valid) v[i] = 0xff800000u;  // -inf: zero-filled / foreign columns never win
+    };
+
+    constexpr int NCH = TC_SW / 32;  // chunks per slice per tile (even)
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const uint32_t bph = (t >> 1) & 1;
       mbar_wait(&S.tfull[buf], bph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + half * (TC_BN / 2);
-      const int n_valid = (int)min((int64_t)(TC_BN / 2), j_end - tile_j0);  // may be <= 0
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + half * (TC_BN / 2));
-#pragma unroll 1
-      for (int c = 0; c < (TC_BN / 2) / 32; ++c) {
-        uint32_t v[32];
-        TC_LD32(v, taddr + c * 32);
-        TC_WAIT_LD(v);
-        const int col0 = c * 32;
-        if (col0 + 32 > n_valid) {
+      const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * TC_SW;
+      const int n_valid = (int)min((int64_t)TC_SW, j_end - tile_j0);  // may be <= 0
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * TC_SW);
+      const int32_t jb0 = (int32_t)tile_j0;
+      uint32_t va[32], vb[32];
+      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+      TC_LD32(va, taddr);
+      TC_WAIT_LD(va);
+      if (n_valid == TC_SW) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i >= n_valid) v[i] = 0xff800000u;  // -inf: zero-filled / foreign columns never win
+        for (int c = 0; c < NCH; c += 2) {
+          TC_LD32(vb, taddr + (c + 1) * 32);
+          process(va, jb0 + c * 32);
+          TC_WAIT_LD(vb);
+          if (c + 2 < NCH) TC_LD32(va, taddr + (c + 2) * 32);
+          process(vb, jb0 + (c + 1) * 32);
+          if (c + 2 < NCH) TC_WAIT_LD(va);
         }
-        const float m = chunk_max(v);
-        if (m >= thr && m > -INFINITY) {
-          r = fmaxf(r, m);
-          thr = r - band;
-          uint32_t pass = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pass |= (__uint_as_float(v[i]) >= thr) ? (1u << i) : 0u;
-          const int32_t jb = (int32_t)(tile_j0 + col0);
-          while (pass) {
-            const int i = __ffs(pass) - 1;
-            pass &= pass - 1;
-            if (cnt == TC_CAP) collapse();
-            list[cnt * TC_BM] = jb + i;
-            ++cnt;
-          }
+      } else {  // last tile of the range: mask the columns beyond j_end
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          if (c > 0) { TC_LD32(va, taddr + c * 32); TC_WAIT_LD(va); }
+          mask_tail(va, c * 32, n_valid);
+          process(va, jb0 + c * 32);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tempty[buf]);
     }
-    collapse();
     if (live) {
-      const int64_t slot = ((int64_t)blockIdx.y * 2 + half) * M + row;
-      part_val[slot] = best;
-      part_idx[slot] = bidx;
+      // hand the surviving chunks of this (split, slice) stream to the refine kernel
+      const int64_t stream = (int64_t)blockIdx.y * TC_SLICES + slice;
+      int k = 0;
+      for (int e = 0; e < cnt; ++e) {
+        const unsigned long long ent = list[e * TC_BM];
+        if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) {
+          if (k < TC_OUT) out_ent[(stream * TC_OUT + k) * M + row] = ent;
+          else spill(ent);
+          ++k;
+        }
+      }
+      out_r[stream * M + row] = r;
+      out_cnt[stream * M + row] = ovf ? -1 : min(k, TC_OUT);
     }
   }
 
@@ -303,9 +349,150 @@ score_select_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const float *_
   }
 }
 
+// Exact re-score of the chunks that did not fit the per-stream lists: one warp per entry
+// (lane = item); the exact winner is merged into row_best[row] with a packed 64-bit atomicMax:
+// (order-preserving float bits << 32) | (0xffffffff - item) -> largest score, then lowest index.
+__device__ __forceinline__ unsigned long long pack_best(float v, int32_t j) {
+  v = v + 0.0f;  // -0 -> +0 so that equal scores compare equal
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
+}
+__device__ __forceinline__ void unpack_best(unsigned long long p, float *v, int32_t *j) {
+  uint32_t b = (uint32_t)(p >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+  *v = __uint_as_float(b);
+  *j = (int32_t)(0xffffffffu - (uint32_t)p);
+}
+
+__global__ void __launch_bounds__(256)
+tc_overflow_kernel(const float *__restrict__ W, int64_t n_rows, const float *__restrict__ Q,
+                   const unsigned int *__restrict__ ovf_count, const unsigned long long *__restrict__ ovf_ent,
+                   const int32_t *__restrict__ ovf_row, unsigned int ovf_cap,
+                   unsigned long long *__restrict__ row_best) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int n = min(*ovf_count, ovf_cap);
+  const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+  for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const int64_t row = ovf_row[i];
+    const int64_t j = (int64_t)(uint32_t)ovf_ent[i] + lane;
+    float best = -INFINITY;
+    int32_t bidx = 0x7fffffff;
+    if (j < n_rows) {
+      const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+      const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
+      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
+      float s = 0.f;
+      s = fmaf(q0.x, w0.x, s); s = fmaf(q0.y, w0.y, s); s = fmaf(q0.z, w0.z, s); s = fmaf(q0.w, w0.w, s);
+      s = fmaf(q1.x, w1.x, s); s = fmaf(q1.y, w1.y, s); s = fmaf(q1.z, w1.z, s); s = fmaf(q1.w, w1.w, s);
+      best = s;
+      bidx = (int32_t)j;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0 && bidx != 0x7fffffff) atomicMax(row_best + row, pack_best(best, bidx));
+  }
+}
+
+// Exact refine: one warp per query row.  R = max over the row's streams of their approximate
+// running maxima; every recorded chunk whose approximate maximum is >= R - band is re-scored
+// item by item (lane = item) with the exact fp32 sequential-k FMA chain; winner =
+// largest exact score, ties -> lowest index.  Streams flagged -1 (too many chunks
+// inside the band, i.e. heavy exact ties) are scanned completely.
+__global__ void __launch_bounds__(256)
+tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
+                 int64_t M, int n_split, int64_t items_per_split, float band_scale,
+                 const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
+                 const unsigned long long *__restrict__ out_ent, const unsigned long long *__restrict__ row_best,
+                 int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int n_streams = n_split * TC_SLICES;
+  float q[TC_D];
+  {
+    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+    q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
+  const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
+  float R = -INFINITY;
+  for (int s = lane; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
+  R = warp_max(R);
+  const float thr = R - band;
+  float best = -INFINITY;
+  int32_t bidx = 0x7fffffff;
+  auto score = [&](int64_t j) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
+    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
+    float s = 0.f;
+    s = fmaf(q[0], w0.x, s); s = fmaf(q[1], w0.y, s); s = fmaf(q[2], w0.z, s); s = fmaf(q[3], w0.w, s);
+    s = fmaf(q[4], w1.x, s); s = fmaf(q[5], w1.y, s); s = fmaf(q[6], w1.z, s); s = fmaf(q[7], w1.w, s);
+    if (s > best || (s == best && (int32_t)j < bidx)) { best = s; bidx = (int32_t)j; }
+  };
+  // lane = stream while the lists are inspected, lane = item while a chunk is re-scored
+  for (int base = 0; base < n_streams; base += 32) {
+    const int s = base + lane;
+    const int cnt = (s < n_streams) ? out_cnt[(int64_t)s * M + row] : 0;
+    unsigned flagged = __ballot_sync(0xffffffffu, cnt < 0);
+    while (flagged) {  // exact scan of a flagged stream's whole column range
+      const int fs = base + __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const int split = fs / TC_SLICES, slice = fs % TC_SLICES;
+      const int64_t j_begin = (int64_t)split * items_per_split;
+      const int64_t j_end = min(n_rows, j_begin + items_per_split);
+      for (int64_t t0 = j_begin + slice * TC_SW; t0 < j_end; t0 += TC_BN)
+        for (int i = lane; i < TC_SW; i += 32)
+          if (t0 + i < j_end) score(t0 + i);
+    }
+#pragma unroll 1
+    for (int e = 0; e < TC_OUT; ++e) {
+      unsigned long long ent = 0;
+      bool pass = false;
+      if (e < cnt) {
+        ent = out_ent[((int64_t)s * TC_OUT + e) * M + row];
+        pass = __uint_as_float((uint32_t)(ent >> 32)) >= thr;
+      }
+      unsigned live = __ballot_sync(0xffffffffu, pass);
+      while (live) {
+        const int src = __ffs(live) - 1;
+        live &= live - 1;
+        const int64_t j = (int64_t)__shfl_sync(0xffffffffu, (uint32_t)ent, src) + lane;
+        if (j < n_rows) score(j);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  if (lane == 0) {
+    const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
+    if (pb) {
+      float ov;
+      int32_t oi;
+      unpack_best(pb, &ov, &oi);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    out_idx[row] = (int64_t)bidx + row_offset;
+    if (out_val) out_val[row] = best;
+  }
+}
+
 // ------------------------------------------------------------------ host side
 struct TcPlan {
   int row_tiles, n_split;
+  unsigned int ovf_cap;
   int64_t items_per_split;
   size_t ws_bytes;
 };
@@ -329,7 +516,11 @@ static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
   const int64_t tps = (tiles + best_ns - 1) / best_ns;
   p->n_split = (int)((tiles + tps - 1) / tps);
   p->items_per_split = tps * TC_BN;
-  p->ws_bytes = (size_t)2 * p->n_split * (size_t)M * (sizeof(float) + sizeof(int32_t));
+  // per (stream, row): running max (4) + count (4) + TC_OUT recorded chunks (8 each);
+  // per row: packed overflow winner (8); overflow buffer: ovf_cap x (8 + 4) + counter
+  const size_t n_sr = (size_t)TC_SLICES * p->n_split * (size_t)M;
+  p->ovf_cap = (unsigned int)(n_sr / 16 < 65536 ? 65536 : (n_sr / 16 > (1u << 24) ? (1u << 24) : n_sr / 16));
+  p->ws_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)M * 8 + (size_t)p->ovf_cap * 12 + 256;
 }
 
 bool score_select_tc_supported(const Table *t) { return t->dim == TC_D && t->tmap_valid; }
@@ -341,27 +532,42 @@ size_t score_select_tc_workspace(const Table *t, int64_t M) {
   return p.ws_bytes;
 }
 
-// Build the TMA descriptor for the table ([n_rows][8] fp32, 32 B rows, SWIZZLE_32B, box 8 x 256).
+// Pre-swizzled image of the table: row j keeps its 32 bytes, with the two 16-byte chunks
+// swapped when bit 2 of j is set (Swizzle<1,4,3>: address bit 4 ^= bit 7).
+__global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, float4 *__restrict__ out) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
+  if (f >= n_rows * 2) return;
+  const int64_t j = f >> 1;
+  const int c = (int)(f & 1);
+  out[j * 2 + (c ^ (int)((j >> 2) & 1))] = W[f];
+}
+
 int table_init_tc(Table *t) {
   t->tmap_valid = 0;
+  t->packed = nullptr;
   if (t->dim != TC_D) return PCV_OK;
-  void *fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+  float *p = nullptr;
+  if (cudaMalloc(&p, (size_t)t->n_rows * TC_D * sizeof(float)) != cudaSuccess) {
     cudaGetLastError();
-    return PCV_OK;  // engine stays unavailable; SIMT engine serves
+    return PCV_OK;  // engine stays unavailable; the SIMT engine serves
   }
-  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  CUtensorMap *map = reinterpret_cast<CUtensorMap *>(t->tmap);
-  cuuint64_t gdim[2] = {(cuuint64_t)TC_D, (cuuint64_t)t->n_rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)(TC_D * sizeof(float))};
-  cuuint32_t box[2] = {(cuuint32_t)TC_D, (cuuint32_t)TC_BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(t->W), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r == CUDA_SUCCESS) t->tmap_valid = 1;
+  const int64_t chunks = t->n_rows * 2;
+  pack_sw32_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(reinterpret_cast<const float4 *>(t->W), t->n_rows,
+                                                              reinterpret_cast<float4 *>(p));
+  count_launch();
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(p);
+    return PCV_OK;
+  }
+  t->packed = p;
+  t->tmap_valid = 1;
   return PCV_OK;
+}
+
+void table_free_tc(Table *t) {
+  if (t->packed) cudaFree(t->packed);
+  t->packed = nullptr;
 }
 
 void launch_select_finalize(const float *pv, const int32_t *pi, int n_parts, int64_t M, int64_t row_offset,
@@ -375,8 +581,16 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     set_error("score_select(tcgen05): workspace too small (%zu < %zu)", ws_bytes, p.ws_bytes);
     return PCV_ERR_WORKSPACE;
   }
-  float *pv = reinterpret_cast<float *>(ws);
-  int32_t *pi = reinterpret_cast<int32_t *>(pv + (size_t)2 * p.n_split * M);
+  const size_t n_sr = (size_t)TC_SLICES * p.n_split * (size_t)M;   // (stream, row) pairs
+  unsigned long long *ent = reinterpret_cast<unsigned long long *>(ws);
+  unsigned long long *row_best = ent + n_sr * TC_OUT;                  // [M]   zeroed below
+  unsigned long long *ovf_ent = row_best + M;                          // [ovf_cap]
+  unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ovf_ent + p.ovf_cap);  // [2] zeroed below (counter + pad)
+  float *rr = reinterpret_cast<float *>(ovf_count + 2);
+  int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);
+  int32_t *ovf_row = cc + n_sr;
+  PCV_CUDA(cudaMemsetAsync(row_best, 0, (size_t)M * 8, st));
+  PCV_CUDA(cudaMemsetAsync(ovf_count, 0, 8, st));
   const size_t smem = sizeof(TcSmem) + 1024;
   static bool attr_set[64] = {false};
   if (!attr_set[t->device & 63]) {
@@ -386,10 +600,15 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
   // |tf32 chain - fp32 chain| <= 1.25 * 2^-9 * |q| * max|w|; the band is twice that
   const float band_scale = 2.0f * 1.25f * 0.001953125f * t->max_row_norm;
   dim3 grid((unsigned)p.row_tiles, (unsigned)p.n_split);
-  score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(t->tmap), t->W,
-                                                         t->n_rows, Q, M, p.items_per_split, band_scale, pv, pi);
+  score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Q, M, p.items_per_split,
+                                                         band_scale, rr, cc, ent, ovf_count, ovf_ent, ovf_row,
+                                                         p.ovf_cap);
   PCV_LAUNCH_CHECK();
-  launch_select_finalize(pv, pi, 2 * p.n_split, M, t->row_offset, out_idx, out_val, st);
+  tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Q, ovf_count, ovf_ent, ovf_row, p.ovf_cap, row_best);
+  PCV_LAUNCH_CHECK();
+  tc_refine_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Q, M, p.n_split,
+                                                           p.items_per_split, band_scale, rr, cc, ent, row_best,
+                                                           out_idx, out_val);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }

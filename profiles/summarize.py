@@ -54,5 +54,30 @@ def full(path):
         print("  --")
 
 
+
+
+def source(path, top=45):
+    """Top SASS lines by stall samples and by executed instructions (ncu --page source)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[1]
+    ci = {h: i for i, h in enumerate(hdr)}
+    body = [r for r in rows[2:] if len(r) == len(hdr)]
+    tot_s = sum(int(r[ci["# Samples"]]) for r in body) or 1
+    tot_i = sum(int(r[ci["Instructions Executed"]]) for r in body) or 1
+    print("# %s: %d SASS lines, %d samples, %d warp-instructions executed" % (path, len(body), tot_s, tot_i))
+    stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    agg = {h: sum(int(r[ci[h]]) for r in body) for h in stall_cols}
+    print("# stall mix:", ", ".join("%s=%.1f%%" % (k[6:], 100.0 * v / tot_s) for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
+    print("# --- in program order, lines with >=0.4%% of samples or >=0.6%% of instructions")
+    for n, r in enumerate(body):
+        s, i = int(r[ci["# Samples"]]), int(r[ci["Instructions Executed"]])
+        if s >= 0.004 * tot_s or i >= 0.006 * tot_i:
+            st = sorted(((int(r[ci[h]]), h[6:]) for h in stall_cols), reverse=True)[:2]
+            print("%5d %-70s samp=%5.1f%% inst=%5.1f%% thr/inst=%4s  %s" % (
+                n, r[ci["Source"]].strip()[:70], 100.0 * s / tot_s, 100.0 * i / tot_i, r[ci["Avg. Threads Executed"]],
+                " ".join("%s:%d" % (b, a) for a, b in st if a)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "source": source}[sys.argv[1]](sys.argv[2])
