@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the slate-generation path.
+
+Two ways the path shards, both one process per GPU over torch.distributed:
+
+* batch data-parallel — rows are independent, the (<= 320 MB) table is replicated,
+  inference needs NO collective (bench.py --gpus N, weak scaling);
+* vocab-parallel — each rank owns a contiguous, 128-aligned row range of the item
+  table; every rank runs the tiny MLPs redundantly on identical inputs/noise, the
+  fused score+select runs on the local shard, and ONE small all-gather of the
+  per-row partial winners (val f32, global idx i64) per scoring step is merged with
+  the reference's tie rule (largest value, equal values -> lowest global index).
+
+The host logic here is backend-agnostic so that the gloo/CPU tests can exercise the
+exchange + merge with a stand-in local scorer.
+"""
+import torch
+import torch.distributed as dist
+
+SHARD_ALIGN = 128  # Philox column blocks and TMA tiles stay aligned across shards
+
+
+def shard_bounds(n_rows, world, rank, align=SHARD_ALIGN):
+    """Contiguous [lo, hi) row range of `rank`; every boundary but the last is a multiple of align."""
+    per = -(-n_rows // world)
+    per = -(-per // align) * align
+    lo = min(rank * per, n_rows)
+    hi = min(lo + per, n_rows)
+    return lo, hi
+
+
+def merge_partials(vals, idx):
+    """vals/idx: [G, M] partial winners in shard order (torch tensors, any device).
+    Winner = largest value, equal values -> lowest global index.  Pure torch (used by the
+    CPU tests; the GPU path calls ops.vp_merge_select)."""
+    G, M = vals.shape
+    best_v, best_i = vals[0].clone(), idx[0].clone()
+    for g in range(1, G):
+        take = (vals[g] > best_v) | ((vals[g] == best_v) & (idx[g] < best_i))
+        best_v = torch.where(take, vals[g], best_v)
+        best_i = torch.where(take, idx[g], best_i)
+    return best_i, best_v
+
+
+class VocabParallelSelector:
+    """score+select over a catalog sharded across the ranks of `group`.
+
+    local_select(Q) -> (idx_global int64[M], val f32[M]) scores the local shard; on a B200 it is
+    ops.score_select on a Table built with row_offset=lo.  merge defaults to the CUDA merge
+    kernel when the partials live on a GPU."""
+
+    def __init__(self, local_select, group=None, merge=None):
+        self.local_select = local_select
+        self.group = group
+        self.merge = merge
+
+    def __call__(self, Q):
+        idx, val = self.local_select(Q)
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return idx, val
+        M = idx.shape[0]
+        # one collective per scoring step: pack (val, idx) into a single int64 buffer
+        packed = torch.empty(2, M, dtype=torch.int64, device=idx.device)
+        packed[0] = val.view(torch.int32).to(torch.int64)
+        packed[1] = idx
+        flat = torch.empty(world * 2, M, dtype=torch.int64, device=idx.device)
+        dist.all_gather_into_tensor(flat, packed, group=self.group)
+        out = flat.view(world, 2, M)
+        vals = out[:, 0].to(torch.int32).view(torch.float32)
+        idxs = out[:, 1].contiguous()
+        merge = self.merge
+        if merge is None:
+            if vals.is_cuda:
+                from . import ops
+                merge = ops.vp_merge_select
+            else:
+                merge = merge_partials
+        return merge(vals.contiguous(), idxs)
+
+
+def shard_table(ops, weight, group=None):
+    """Build the local ops.Table for this rank's shard of `weight` ([N, D] on this rank's GPU)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(weight.shape[0], world, rank)
+    return ops.Table(weight[lo:hi].contiguous(), row_offset=lo), lo, hi
