@@ -44,6 +44,9 @@ const char *pcv_last_error(void);
 int pcv_device_ok(int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t pcv_launch_count(void);
+/* *counter += inc on the stream: advances the device-side Philox row counter between the
+ * replays of a captured CUDA graph (see offset_dev below). */
+int pcv_counter_add(uint64_t *counter, uint64_t inc, pcv_stream_t stream);
 
 /* ------------------------------------------------------------------ */
 /* Item table (the frozen, row-L2-normalised catalog; cvae.py:27-33)   */
@@ -80,6 +83,8 @@ typedef struct {
   uint64_t seed;      /* exprace with noise==NULL: Philox4x32-10 key               */
   uint64_t offset;    /* Philox stream offset (added to the row counter word)      */
   int no_repeat;      /* reserved: must be 0 (the reference has no mask) */
+  const uint64_t *offset_dev; /* optional DEVICE counter added to `offset` at run time, so a
+                                 captured CUDA graph draws fresh noise on every replay  */
 } pcv_select_opts;
 
 int pcv_score_select_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
@@ -163,6 +168,7 @@ typedef struct {
   uint64_t seed, offset;
   float *z;       /* [B, latent] */
   float *eps_out; /* optional [B, latent]: the eps actually used (for backward) */
+  const uint64_t *offset_dev; /* optional device counter added to `offset` (CUDA-graph replays) */
 } pcv_mlp_desc;
 
 int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream);
@@ -187,14 +193,13 @@ typedef struct {
   double keep_prob;        /* n_neg / N; >= 1 means full-catalog soft-max, no RNG    */
   const uint32_t *bitmask; /* parity mode: [M, ceil(N/32)] bit j%32 of word j/32 = Bernoulli draw (target is OR-ed in by the kernel) */
   uint64_t seed, offset;   /* Philox mode (bitmask == NULL && keep_prob < 1)         */
+  const uint64_t *offset_dev; /* optional device counter added to `offset` (CUDA-graph replays) */
 } pcv_ce_mask;
 
 int pcv_ce_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
 /* Single streaming pass producing loss rows, log-sum-exp and dq (forward and
  * the gradient in one pass; backward is a scale by the upstream gradient).
- * For vocab-parallel shards targets outside [row_offset, row_offset+n_rows) are
- * skipped and partial (max, sumexp, target_logit, dq_unnormalised) are returned
- * through pcv_ce_partial instead. */
+ * (Vocab-parallel CE partials are not exposed yet: the table must have row_offset 0.) */
 int pcv_ce_fwd_bwd(const pcv_table *t, const float *Q, const int64_t *targets,
                    int64_t M, const pcv_ce_mask *mask, float *loss_rows, float *lse,
                    float *dq, void *workspace, size_t workspace_bytes,

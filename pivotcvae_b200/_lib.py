@@ -31,7 +31,7 @@ class PcvError(RuntimeError):
 
 class SelectOpts(ctypes.Structure):
     _fields_ = [("mode", c_int), ("engine", c_int), ("noise", c_void_p), ("seed", c_uint64),
-                ("offset", c_uint64), ("no_repeat", c_int)]
+                ("offset", c_uint64), ("no_repeat", c_int), ("offset_dev", c_void_p)]
 
 
 class Linear(ctypes.Structure):
@@ -48,12 +48,13 @@ class MlpDesc(ctypes.Structure):
                 ("layer", Linear * PCV_MAX_LAYERS), ("out", c_void_p), ("out_ld", c_int),
                 ("out_col0", c_int), ("copy_seg", c_int), ("x0", c_void_p),
                 ("acts", c_void_p * PCV_MAX_LAYERS), ("latent", c_int), ("eps", c_void_p),
-                ("seed", c_uint64), ("offset", c_uint64), ("z", c_void_p), ("eps_out", c_void_p)]
+                ("seed", c_uint64), ("offset", c_uint64), ("z", c_void_p), ("eps_out", c_void_p),
+                ("offset_dev", c_void_p)]
 
 
 class CeMask(ctypes.Structure):
     _fields_ = [("keep_prob", ctypes.c_double), ("bitmask", c_void_p), ("seed", c_uint64),
-                ("offset", c_uint64)]
+                ("offset", c_uint64), ("offset_dev", c_void_p)]
 
 
 class UrmDesc(ctypes.Structure):
@@ -67,6 +68,7 @@ EXPORTS = {
     "pcv_last_error": (ctypes.c_char_p, []),
     "pcv_device_ok": (c_int, [c_int]),
     "pcv_launch_count": (c_int64, []),
+    "pcv_counter_add": (c_int, [c_void_p, c_uint64, c_void_p]),
     "pcv_table_create": (c_int, [c_void_p, c_int64, c_int, c_int64, ctypes.POINTER(c_void_p)]),
     "pcv_table_destroy": (None, [c_void_p]),
     "pcv_normalize_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

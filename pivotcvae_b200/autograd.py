@@ -21,10 +21,11 @@ class MlpSpec:
     """
 
     def __init__(self, segs, acts, latent=0, eps=None, seed=0, offset=0, out_ld=None, out_col0=0, copy_seg=-1,
-                 save=True):
+                 save=True, offset_dev=None):
         self.segs, self.acts = segs, list(acts)
         self.save = save
         self.latent, self.eps, self.seed, self.offset = latent, eps, seed, offset
+        self.offset_dev = offset_dev
         self.out_ld, self.out_col0, self.copy_seg = out_ld, out_col0, copy_seg
 
     def build_segments(self, dense):
@@ -59,7 +60,7 @@ class FusedMLPFn(torch.autograd.Function):
         segments = spec.build_segments(dense)
         res = ops.mlp_forward(segments, layers, B, out_ld=spec.out_ld, out_col0=spec.out_col0,
                               copy_seg=spec.copy_seg, save=need, latent=spec.latent, eps=spec.eps,
-                              seed=spec.seed, offset=spec.offset)
+                              seed=spec.seed, offset=spec.offset, offset_dev=spec.offset_dev)
         ctx.spec, ctx.n_dense, ctx.n_layers = spec, n_dense, len(layers)
         ctx.n_out = layers[-1][0].shape[0]
         if need:
@@ -118,9 +119,9 @@ class CatalogCEFn(torch.autograd.Function):
     (train_generative.py:36-42, 59) without materialising logits."""
 
     @staticmethod
-    def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset):
+    def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset, offset_dev=None):
         loss_rows, lse, dq = ops.ce_fwd_bwd(table, q, targets, keep_prob, bitmask, seed, offset,
-                                            want_dq=q.requires_grad)
+                                            want_dq=q.requires_grad, offset_dev=offset_dev)
         ctx.M = q.shape[0]
         if dq is not None:
             ctx.save_for_backward(dq)
@@ -134,7 +135,7 @@ class CatalogCEFn(torch.autograd.Function):
         d = dq * scale
         if g_rows is not None:
             d = d + dq * g_rows.unsqueeze(1)
-        return d, None, None, None, None, None, None
+        return d, None, None, None, None, None, None, None
 
 
 class KLFn(torch.autograd.Function):

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(CE_THREADS, 2)
 ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
           const float *__restrict__ Q, const int64_t *__restrict__ targets, int64_t M,
           int64_t items_per_split, const uint32_t *__restrict__ bitmask, int64_t mask_words,
-          uint64_t seed, uint64_t offset, uint32_t thresh, float *__restrict__ part) {
+          uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_dev, uint32_t thresh,
+          float *__restrict__ part) {
+  if (MODE == CE_PHILOX && offset_dev) offset += *offset_dev;
   using Cfg = CECfg<D>;
   constexpr int R = Cfg::R, TILE = Cfg::TILE, C4 = Cfg::C4, REC = 3 + D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -275,7 +277,7 @@ __global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, 
 template <int D, int MODE>
 static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
                      int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
-                     uint64_t offset, uint32_t thresh, float *part, cudaStream_t st) {
+                     uint64_t offset, const uint64_t *offset_dev, uint32_t thresh, float *part, cudaStream_t st) {
   using Cfg = CECfg<D>;
   auto kern = ce_kernel<D, MODE>;
   static bool attr_set[64] = {false};
@@ -286,7 +288,7 @@ static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int6
   dim3 grid((unsigned)p.row_tiles, (unsigned)p.n_split);
   kern<<<grid, CE_THREADS, Cfg::SMEM, st>>>(t->W, t->n_rows, t->row_offset, Q, targets, M,
                                             p.items_per_split, bitmask, mask_words, seed, offset,
-                                            thresh, part);
+                                            offset_dev, thresh, part);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }
@@ -294,13 +296,14 @@ static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int6
 template <int MODE>
 static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
                        int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
-                       uint64_t offset, uint32_t thresh, float *part, cudaStream_t st) {
+                       uint64_t offset, const uint64_t *offset_dev, uint32_t thresh, float *part,
+                       cudaStream_t st) {
   switch (t->dim) {
-    case 4: return launch_ce<4, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
-    case 8: return launch_ce<8, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
-    case 16: return launch_ce<16, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
-    case 32: return launch_ce<32, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
-    case 64: return launch_ce<64, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, thresh, part, st);
+    case 4: return launch_ce<4, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
+    case 8: return launch_ce<8, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
+    case 16: return launch_ce<16, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
+    case 32: return launch_ce<32, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
+    case 64: return launch_ce<64, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
   }
   set_error("ce: dim %d unsupported (use 4, 8, 16, 32 or 64)", t->dim);
   return PCV_ERR_UNSUPPORTED;
@@ -349,14 +352,14 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t mask_words = (t->n_rows + 31) / 32;
   if (mask->bitmask) {
-    rc = ce_dispatch<CE_BITMASK>(t, p, Q, targets, M, mask->bitmask, mask_words, 0, 0, 0, part, st);
+    rc = ce_dispatch<CE_BITMASK>(t, p, Q, targets, M, mask->bitmask, mask_words, 0, 0, nullptr, 0, part, st);
   } else if (mask->keep_prob >= 1.0) {
-    rc = ce_dispatch<CE_DENSE>(t, p, Q, targets, M, nullptr, 0, 0, 0, 0, part, st);
+    rc = ce_dispatch<CE_DENSE>(t, p, Q, targets, M, nullptr, 0, 0, 0, nullptr, 0, part, st);
   } else {
     double th32 = mask->keep_prob * 4294967296.0;
     uint32_t thresh = th32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)th32;
-    rc = ce_dispatch<CE_PHILOX>(t, p, Q, targets, M, nullptr, 0, mask->seed, mask->offset, thresh,
-                                part, st);
+    rc = ce_dispatch<CE_PHILOX>(t, p, Q, targets, M, nullptr, 0, mask->seed, mask->offset, mask->offset_dev,
+                                thresh, part, st);
   }
   if (rc != PCV_OK) return rc;
   ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(

@@ -249,6 +249,7 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
   // ---------------- reparameterisation epilogue ----------------
   if (d.latent > 0) {
     const int Z = d.latent;
+    const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
     for (int e = tid; e < BM * Z; e += MLP_THREADS) {
       const int row = e / Z, j = e - row * Z;
       const int64_t b = b0 + row;
@@ -260,7 +261,7 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
         eps = d.eps[b * Z + j];
       } else {
         float n4[4];
-        normal4(d.seed, d.offset, b, j >> 2, n4);
+        normal4(d.seed, rng_off, b, j >> 2, n4);
         eps = n4[j & 3];
       }
       const float sd = pcv_expf(lv * 0.5f);

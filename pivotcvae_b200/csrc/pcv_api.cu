@@ -52,6 +52,8 @@ __global__ void max_row_norm2_kernel(const float *__restrict__ W, int64_t n, int
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(ss));
 }
 
+__global__ void counter_add_kernel(unsigned long long *c, unsigned long long inc) { *c += inc; }
+
 int table_init_tc(Table *t);  // score_select_tc.cu
 void table_free_tc(Table *t);
 
@@ -64,6 +66,13 @@ extern "C" {
 int pcv_abi_version(void) { return PCV_ABI_VERSION; }
 const char *pcv_last_error(void) { return g_err; }
 int64_t pcv_launch_count(void) { return g_launches.load(); }
+
+int pcv_counter_add(uint64_t *counter, uint64_t inc, pcv_stream_t stream) {
+  PCV_CHECK_ARG(counter != nullptr, "counter is NULL");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(counter), inc);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
 
 int pcv_device_ok(int device) {
   int major = 0, minor = 0;

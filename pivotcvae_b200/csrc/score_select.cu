@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(SS_THREADS, (D <= 32 ? 2 : 1))
 score_select_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
                     const float *__restrict__ Q, int64_t M, int64_t items_per_split,
                     const float *__restrict__ noise, uint64_t seed, uint64_t offset,
-                    float *__restrict__ part_val, int32_t *__restrict__ part_idx,
-                    float *__restrict__ logits_out) {
+                    const uint64_t *__restrict__ offset_dev, float *__restrict__ part_val,
+                    int32_t *__restrict__ part_idx, float *__restrict__ logits_out) {
+  if (MODE == SS_EXPRACE_PHILOX && offset_dev) offset += *offset_dev;
   using Cfg = SSCfg<D>;
   constexpr int R = Cfg::R, TILE = Cfg::TILE, C4 = Cfg::C4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -298,8 +299,8 @@ __global__ void philox_exponential_kernel(uint64_t seed, uint64_t offset, int64_
 
 template <int D, int MODE>
 static int launch_ss(const Table *t, const SSPlan &p, const float *Q, int64_t M,
-                     const float *noise, uint64_t seed, uint64_t offset, float *pv, int32_t *pi,
-                     float *logits, cudaStream_t st) {
+                     const float *noise, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                     float *pv, int32_t *pi, float *logits, cudaStream_t st) {
   using Cfg = SSCfg<D>;
   auto kern = score_select_kernel<D, MODE>;
   static bool attr_set[64] = {false};  // per instantiation, per device
@@ -309,22 +310,22 @@ static int launch_ss(const Table *t, const SSPlan &p, const float *Q, int64_t M,
   }
   dim3 grid((unsigned)p.row_tiles, (unsigned)p.n_split);
   kern<<<grid, SS_THREADS, Cfg::SMEM, st>>>(t->W, t->n_rows, t->row_offset, Q, M,
-                                             p.items_per_split, noise, seed, offset, pv, pi, logits);
+                                             p.items_per_split, noise, seed, offset, offset_dev, pv, pi, logits);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }
 
 template <int MODE>
 static int dispatch_dim(const Table *t, const SSPlan &p, const float *Q, int64_t M,
-                        const float *noise, uint64_t seed, uint64_t offset, float *pv,
-                        int32_t *pi, float *logits, cudaStream_t st) {
+                        const float *noise, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                        float *pv, int32_t *pi, float *logits, cudaStream_t st) {
   switch (t->dim) {
-    case 4: return launch_ss<4, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
-    case 8: return launch_ss<8, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
-    case 16: return launch_ss<16, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
-    case 32: return launch_ss<32, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
-    case 64: return launch_ss<64, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
-    case 128: return launch_ss<128, MODE>(t, p, Q, M, noise, seed, offset, pv, pi, logits, st);
+    case 4: return launch_ss<4, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
+    case 8: return launch_ss<8, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
+    case 16: return launch_ss<16, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
+    case 32: return launch_ss<32, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
+    case 64: return launch_ss<64, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
+    case 128: return launch_ss<128, MODE>(t, p, Q, M, noise, seed, offset, offset_dev, pv, pi, logits, st);
   }
   set_error("score_select: dim %d unsupported (use 4, 8, 16, 32, 64 or 128)", t->dim);
   return PCV_ERR_UNSUPPORTED;
@@ -403,13 +404,13 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
   int32_t *pi = reinterpret_cast<int32_t *>(pv + (size_t)p.n_split * M);
 
   if (opts->mode == PCV_SELECT_GREEDY) {
-    rc = dispatch_dim<SS_GREEDY>(t, p, Q, M, nullptr, 0, 0, pv, pi, nullptr, st);
+    rc = dispatch_dim<SS_GREEDY>(t, p, Q, M, nullptr, 0, 0, nullptr, pv, pi, nullptr, st);
   } else if (opts->noise) {
-    rc = dispatch_dim<SS_EXPRACE_NOISE>(t, p, Q, M, opts->noise, 0, 0, pv, pi, nullptr, st);
+    rc = dispatch_dim<SS_EXPRACE_NOISE>(t, p, Q, M, opts->noise, 0, 0, nullptr, pv, pi, nullptr, st);
   } else {
     PCV_CHECK_ARG(t->row_offset % 128 == 0, "Philox exprace needs row_offset % 128 == 0");
-    rc = dispatch_dim<SS_EXPRACE_PHILOX>(t, p, Q, M, nullptr, opts->seed, opts->offset, pv, pi,
-                                         nullptr, st);
+    rc = dispatch_dim<SS_EXPRACE_PHILOX>(t, p, Q, M, nullptr, opts->seed, opts->offset, opts->offset_dev,
+                                         pv, pi, nullptr, st);
   }
   if (rc != PCV_OK) return rc;
   int threads = 256;
@@ -432,7 +433,7 @@ int pcv_score_logits(const pcv_table *th, const float *Q, int64_t M, float *out,
     set_error("score_logits: dim %d unsupported", t->dim);
     return PCV_ERR_UNSUPPORTED;
   }
-  return dispatch_dim<SS_LOGITS>(t, p, Q, M, nullptr, 0, 0, nullptr, nullptr, out,
+  return dispatch_dim<SS_LOGITS>(t, p, Q, M, nullptr, 0, 0, nullptr, nullptr, nullptr, out,
                                  (cudaStream_t)stream);
 }
 

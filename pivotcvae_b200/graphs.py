@@ -1,0 +1,53 @@
+"""CUDA-graph capture of the slate-generation step (launch-bound inner loop -> one graph launch).
+
+GraphedSlateGenerator captures `model.recommend(ctx, users, return_item=True)` followed by the
+response model's score of the generated slates into ONE CUDA graph over static buffers.  Random
+draws stay fresh on every replay: the Philox row counter lives in device memory
+(pcv_*.offset_dev) and the last node of the graph advances it (pcv_counter_add).
+"""
+import torch
+
+from . import ops
+
+
+class GraphedSlateGenerator:
+    def __init__(self, model, env, batch, warmup=3):
+        dev = model.docEmbed.weight.device
+        self.model, self.env, self.batch = model, env, batch
+        L = model.slate_size
+        self.ctx = torch.zeros(batch, L, device=dev)
+        self.users = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.no_user = model.noUser
+        model.noise.begin_graph(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):     # builds the table handle, workspaces, smem attributes
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.items, self.z_mu, self.resp = self._step()
+        self.launches_per_step = ops.launch_count() - l0
+
+    def _step(self):
+        items, z_mu = self.model.recommend(self.ctx, None if self.no_user else self.users, return_item=True)
+        resp = self.env(items.view(self.batch, -1), self.users)
+        self.model.noise.end_graph_step()
+        return items, z_mu, resp
+
+    def load_inputs(self, ctx, users=None):
+        self.ctx.copy_(ctx, non_blocking=True)
+        if users is not None:
+            self.users.copy_(users, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.items, self.resp
+
+    def __call__(self, ctx, users=None):
+        """-> (items int64[B*L], resp f32[B, L]) in static buffers (overwritten by the next call)."""
+        self.load_inputs(ctx, users)
+        return self.replay()

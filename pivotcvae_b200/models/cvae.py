@@ -91,8 +91,7 @@ class BaseCVAE(nn.Module):
         eps = self.noise.pop("eps")
         if eps is not None:
             return dict(eps=eps.to(self.docEmbed.weight.device))
-        seed, off = self.noise.next_stream(B)
-        return dict(seed=seed, offset=off)
+        return self.noise.stream_args(B)
 
     # ---- reference API
     def encode(self, emb, c, u_emb=None):

@@ -64,8 +64,8 @@ class UserPivotCVAE(BaseCVAE):
         noise = self.noise.pop("race")
         if noise is not None:
             return ops.score_select(self.item_table(), q, "exprace", noise=noise.to(self._dev()), want_val=False)[0]
-        seed, off = self.noise.next_stream(q.shape[0])
-        return ops.score_select(self.item_table(), q, "exprace", seed=seed, offset=off, want_val=False)[0]
+        return ops.score_select(self.item_table(), q, "exprace", want_val=False,
+                                **self.noise.stream_args(q.shape[0]))[0]
 
     def pick_pivot(self, pivot_output, true_pivot=[]):
         return self.docEmbed.weight[self._pick_index(pivot_output, true_pivot)]

@@ -17,7 +17,31 @@ class NoiseSource:
     def __init__(self, seed=None):
         self.seed = seed
         self.counter = 0
+        self.device_counter = None   # int64[1] CUDA tensor while a CUDA graph is captured / replayed
         self._queue = {"eps": [], "race": [], "mask": []}
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["device_counter"] = None
+        return st
+
+    # ---- CUDA-graph mode: offsets inside the captured step are relative, the base lives on the
+    # device and is advanced by one tiny kernel at the end of every replay (pcv_counter_add)
+    def begin_graph(self, device):
+        import torch as _t
+        if self.seed is None:
+            self.seed = int(_t.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.device_counter = _t.full((1,), self.counter, dtype=_t.int64, device=device)
+        self._graph_base = self.counter
+        self.counter = 0
+
+    def end_graph_step(self):
+        """Call as the last op of the captured step: advances the device counter by the rows consumed."""
+        from . import ops
+        used = self.counter
+        ops.counter_add(self.device_counter, used)
+        self.counter = 0
+        return used
 
     def push(self, kind, tensor):
         self._queue[kind].append(tensor)
@@ -36,3 +60,11 @@ class NoiseSource:
         off = self.counter
         self.counter += int(rows)
         return self.seed, off
+
+    def stream_args(self, rows):
+        """kwargs (seed, offset[, offset_dev]) for one op consuming `rows` Philox row counters."""
+        seed, off = self.next_stream(rows)
+        kw = dict(seed=seed, offset=off)
+        if self.device_counter is not None:
+            kw["offset_dev"] = self.device_counter
+        return kw

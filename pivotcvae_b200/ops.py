@@ -143,7 +143,14 @@ def normalize_rows(W):
 # ----------------------------------------------------------------------------
 # score + select
 # ----------------------------------------------------------------------------
-def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="auto", want_val=True):
+def counter_add(counter, inc):
+    """counter (int64[1] CUDA tensor) += inc on the current stream (Philox row counter of graph replays)."""
+    with torch.cuda.device(counter.device):
+        L.check(L.load().pcv_counter_add(_ptr(counter), int(inc), _stream()), "pcv_counter_add")
+
+
+def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="auto", want_val=True,
+                 offset_dev=None):
     """-> (idx int64[M], val f32[M]).  mode 'greedy' | 'exprace'."""
     Q = _f32(Q, "Q")
     M, D = Q.shape
@@ -158,6 +165,7 @@ def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="
             raise L.PcvError("noise must be [M, n_rows]")
     opts.noise = noise.data_ptr() if noise is not None else None
     opts.seed, opts.offset, opts.no_repeat = int(seed), int(offset), 0
+    opts.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
     idx = torch.empty(M, dtype=torch.int64, device=Q.device)
     val = torch.empty(M, dtype=torch.float32, device=Q.device) if want_val else None
     ws = table.workspace("select", M)
@@ -241,7 +249,7 @@ class Gather:
 
 
 def mlp_forward(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
-                latent=0, eps=None, seed=0, offset=0):
+                latent=0, eps=None, seed=0, offset=0, offset_dev=None):
     """Run one fused MLP block.
 
     segments: list of Dense/OneHot/Gather; layers: list of (W[n_out,n_in], b[n_out], act).
@@ -295,6 +303,7 @@ def mlp_forward(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_
             d.eps_out = eo.data_ptr()
             res["eps"] = eo
         d.seed, d.offset = int(seed), int(offset)
+        d.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
     with torch.cuda.device(dev), _timed("mlp_fwd"):
         L.check(L.load().pcv_mlp_fwd(ctypes.byref(d), int(B), _stream()), "pcv_mlp_fwd")
     return res
@@ -313,7 +322,7 @@ def kl_fwd_bwd(mu, logvar, pmu, plogvar, grads=True):
     return out, g
 
 
-def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0, want_dq=True):
+def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0, want_dq=True, offset_dev=None):
     """-> (loss_rows[M], lse[M], dq[M, D] or None); see include/pcv_b200.h."""
     Q, targets = _f32(Q, "Q"), _i64(targets, "targets").reshape(-1)
     M, D = Q.shape
@@ -327,6 +336,7 @@ def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0,
             raise L.PcvError("bitmask must be int32/uint32 [M, ceil(N/32)]")
         mask.bitmask = bitmask.data_ptr()
     mask.seed, mask.offset = int(seed), int(offset)
+    mask.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
     loss = torch.empty(M, dtype=torch.float32, device=Q.device)
     lse = torch.empty(M, dtype=torch.float32, device=Q.device)
     dq = torch.empty(M, D, dtype=torch.float32, device=Q.device) if want_dq else None

@@ -50,10 +50,11 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
     keep = float(n_neg) / float(N)
     bitmask = model.noise.pop("mask")
     M = slates.numel()
-    seed, off = (0, 0)
+    kw = dict(seed=0, offset=0)
     if bitmask is None and keep < 1.0:
-        seed, off = model.noise.next_stream(M)
-    recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, seed, off)
+        kw = model.noise.stream_args(M)
+    recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, kw["seed"],
+                                      kw["offset"], kw.get("offset_dev"))
     KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
     loss = recLoss + beta * KLD
     return loss, recLoss, KLD
