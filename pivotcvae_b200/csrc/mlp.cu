@@ -17,7 +17,7 @@
 //
 // Layout: a CTA owns BM = 8/16/32 batch rows; activations ping-pong between two
 // transposed shared-memory buffers actT[k][row]; each layer's weights stream through
-// a double-buffered [16][256] shared-memory stage (transposed on the fly from
+// a double-buffered [32][256] shared-memory stage (transposed on the fly from
 // nn.Linear's [n_out][n_in], prefetched one chunk ahead in registers); a thread
 // accumulates an 8-row x CT-column register tile.
 #include "pcv_common.cuh"
@@ -25,7 +25,7 @@
 namespace pcv {
 
 constexpr int MLP_THREADS = 256;
-constexpr int MLP_KC = 16;    // k-chunk staged per step
+constexpr int MLP_KC = 32;    // k-chunk staged per step
 constexpr int MLP_NB = 256;   // output columns per pass
 constexpr int MLP_WLD = MLP_NB + 4;
 
@@ -98,9 +98,6 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
 #pragma unroll
         for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = (kc + kk < K) ? __ldg(wrow + kk) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = 0.f;
     }
   };
   auto advance = [&]() {  // -> false when the stream is exhausted
@@ -189,16 +186,18 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
 
       for (int kc = 0; kc < K; kc += MLP_KC) {
         float *ws = wst + buf * (MLP_KC * MLP_WLD);
+        if (nb + tid < L.n_out) {   // narrow layers: only the threads that own a real column stage it
 #pragma unroll
-        for (int kk = 0; kk < MLP_KC; ++kk) ws[kk * MLP_WLD + tid] = wv[kk];
+          for (int kk = 0; kk < MLP_KC; ++kk) ws[kk * MLP_WLD + tid] = wv[kk];
+        }
         __syncthreads();
         if (more) {
           more = advance();
           if (more) fetch(pl, pnb, pkc);   // next chunk's loads fly during this chunk's FMAs
         }
-        const int kmax = min(MLP_KC, K - kc);
+        const int kmax = (nb + cg * CT < L.n_out) ? min(MLP_KC, K - kc) : 0;   // idle column groups skip the FMAs
         const float *ap = cur + (size_t)kc * ALD + rg * 8;
-        for (int kk = 0; kk < kmax; ++kk) {
+        auto fma_step = [&](int kk) {
           const float4 a0 = *reinterpret_cast<const float4 *>(ap + kk * ALD);
           const float4 a1 = *reinterpret_cast<const float4 *>(ap + kk * ALD + 4);
           float w[CT];
@@ -216,6 +215,13 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
           for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
+        };
+        if (kmax == MLP_KC) {
+          // full chunk: straight-line code so the shared-memory loads are hoisted ahead of the FMAs
+#pragma unroll
+          for (int kk = 0; kk < MLP_KC; ++kk) fma_step(kk);
+        } else {
+          for (int kk = 0; kk < kmax; ++kk) fma_step(kk);
         }
         buf ^= 1;
       }

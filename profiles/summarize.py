@@ -62,7 +62,13 @@ def source(path, top=45):
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
-    body = [r for r in rows[2:] if len(r) == len(hdr)]
+    body = []
+    for r in rows[2:]:
+        if len(r) != len(hdr) or r[0] == hdr[0]:
+            if body:
+                break          # only the first captured launch
+            continue
+        body.append(r)
     tot_s = sum(int(r[ci["# Samples"]]) for r in body) or 1
     tot_i = sum(int(r[ci["Instructions Executed"]]) for r in body) or 1
     print("# %s: %d SASS lines, %d samples, %d warp-instructions executed" % (path, len(body), tot_s, tot_i))
