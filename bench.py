@@ -32,6 +32,8 @@ WORKLOADS = {
                desc="C1 ML-1M shape: 3707 items, 6041 users, slate 5, dim 8, with user, B=64"),
     "c2": dict(n_items=50000, n_users=1, L=10, D=8, Z=16, H=256, PH=128, no_user=True, B=1024,
                desc="C2 Yoochoose shape: 50k items, slate 10, dim 8, nouser, B=1024, PivotCVAE gt_pi + response MLP"),
+    "c3": dict(n_items=100000, n_users=6041, L=5, D=8, Z=16, H=256, PH=128, no_user=False, B=4096,
+               desc="C3: PivotCVAE gt training, fused full-catalog soft-max CE + KL, 100k items, slate 5, dim 8, B=4096"),
     "c4": dict(n_items=1000000, n_users=6041, L=5, D=8, Z=16, H=256, PH=128, no_user=False, B=4096,
                desc="C4: 1M items, slate 5, dim 8, with user, B=4096 (replicated table, batch data-parallel)"),
 }
@@ -224,6 +226,128 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------ GPU arm
+def make_train_batch(w, B, step, seed=4321):
+    """Synthetic (slate, user, response) rows: uniform items/users, Bernoulli(0.5) responses."""
+    g = torch.Generator().manual_seed(seed + step)
+    slates = torch.randint(0, w["n_items"], (B, w["L"]), generator=g)
+    users = torch.randint(0, w["n_users"], (B, 1), generator=g)
+    resp = (torch.rand(B, w["L"], generator=g) < 0.5).float()
+    return {"slates": slates, "users": users, "responses": resp}
+
+
+def run_train(args, w):
+    """train samples/sec: get_gen_loss (prior + encoder + decoder + fused catalog CE + KL) -> backward -> Adam.step,
+    per step one batch; n_neg = --n-neg (N = full-catalog soft-max, the C3 config; 1000 = the reference default)."""
+    import torch.distributed as dist
+    from pivotcvae_b200 import ops
+    from pivotcvae_b200.train_generative import get_gen_loss
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    B, K, W = (args.batch or w["B"]), args.steps, args.warmup
+    sd, env_sd = make_weights(w, "pivot")
+    model, _ = build_gpu(w, sd, env_sd, "greedy", device)
+    model.noise.reseed(99 + rank)
+    n_neg = w["n_items"] if args.n_neg <= 0 else args.n_neg
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    params = [p for p in model.parameters() if p.requires_grad]
+    batches = [make_train_batch(w, B, i, seed=4321 + 7919 * rank) for i in range(K + W)]
+    dev_batches = [{k: v.to(device) for k, v in b.items()} for b in batches]
+    pin_batches = [{k: v.pin_memory() for k, v in b.items()} for b in batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss, rec, kld = get_gen_loss(batch, model, None, 0.001, n_neg=n_neg)
+        loss.backward()
+        if world > 1:      # data-parallel: one all-reduce of the (~270k fp32) MLP gradients per step
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for p in params:
+                if p.grad is not None:
+                    n = p.grad.numel()
+                    p.grad.copy_(flat[o:o + n].view_as(p.grad))
+                    o += n
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(dev_batches[i])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with ops.KernelTimer() as kt:
+        for i in range(K):
+            flush.zero_()
+            ev[i][0].record()
+            step(dev_batches[W + i])
+            ev[i][1].record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ksum = kt.summary()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        ev2[i][0].record()
+        b = {k: v.to(device, non_blocking=True) for k, v in pin_batches[W + i].items()}
+        loss = step(b)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+        ev2[i][1].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms, ms_e2e = float(t[0]), float(t[1])
+    total = B * world * K
+    L_, D, N = w["L"], w["D"], w["n_items"]
+    dom = ksum.get("ce_fwd_bwd", {"ms_avg": float("nan"), "calls": 0})
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    keep = n_neg / N
+    flops = (2.0 * D * N * B * L_ + 2.0 * D * N * B * (L_ - 1)) * keep   # logits + dq accumulation over kept items
+    ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
+    line = {"metric": "train samples/sec (PivotCVAE gt, fused catalog CE + KL, fwd+bwd+Adam)", "value": total / (ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "batch_per_gpu": B, "n_neg": n_neg, "beta": 0.001,
+                       "parallelism": "dp%d (replicated table, grad all-reduce)" % world,
+                       "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed"},
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(B * L_ * 8 + B * 8 + B * L_ * 4), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "ce_kernel<D=%d> (+finalize), M=%d rows x N=%d items, keep=%.4f" % (D, B * L_, N, keep),
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "ms_avg_launch": dom["ms_avg"], "share_of_step": dom["ms_avg"] / (ms / K) if dom["calls"] else None,
+                         "per_call_ms": {k: round(v["ms_avg"], 4) for k, v in ksum.items()}},
+            "cpu_baseline": None, "clocks": clk}
+    print(json.dumps(line))
+
+
 def run_ours(args, w):
     import torch.distributed as dist
     from pivotcvae_b200 import ops
@@ -366,7 +490,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="greedy", choices=["greedy", "sampled", "list"])
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "sampled", "list", "train"])
+    ap.add_argument("--n-neg", type=int, default=0, help="train mode: negatives per row (0 = the whole catalog)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=256, help="slates per step of the CPU arm (bounded sample)")
@@ -376,6 +501,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif args.mode == "train":
+        run_train(args, w)
     else:
         run_ours(args, w)
 

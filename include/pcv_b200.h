@@ -185,7 +185,10 @@ int pcv_kl_fwd_bwd(const float *mu, const float *logvar, const float *pmu,
 /*   train_generative.py:36-42 (downsample), :59 (CrossEntropyLoss),   */
 /*   pivotcvae.py:274 (logits) — logits never reach HBM.               */
 /* loss_row[i] = log(sum_{j in mask_i} e^{x_ij} + (N-|mask_i|)) - x_{i,t_i}   */
-/* mask_i = {t_i} U Bernoulli(keep_prob) per (i, j); masked-out logits are 0 */
+/* mask_i = {t_i} U Bernoulli(keep_prob) per (i, j); masked-out logits are 0.   */
+/* Philox mode draws the mask as a gap process (Geometric(keep) distances inside */
+/* 1024-column blocks, integer inverse CDF) and visits only the kept columns:    */
+/* O(n_neg) work per row instead of O(N).                                        */
 /* (not -inf) exactly as `pred * mask` does.               */
 /* dq[i,:] = d loss_row[i] / d q_i  (the table is frozen: no dW).      */
 /* ------------------------------------------------------------------ */

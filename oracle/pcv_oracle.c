@@ -130,16 +130,46 @@ void orc_exprace_uniform(uint64_t seed, uint64_t offset, int64_t M, int64_t n_co
     }
 }
 
-/* Bernoulli(keep_prob) bitmask of the CE Philox mode: bit (j & 31) of word j >> 5. */
+/* Bernoulli(keep_prob) bitmask of the CE Philox mode (train_generative.py:39), bit (j & 31) of
+ * word j >> 5.  The library draws it as a gap process: inside every block of 1024 consecutive
+ * columns the distance to the next kept column is Geometric(keep) (memoryless => the columns are
+ * i.i.d. Bernoulli(keep)).  Gap = #{g in 1..1024 : u < T[g]}, T[g] = floor(T[g-1] * q32 / 2^32),
+ * T[0] = 2^32, q32 = round((1-keep) * 2^32); u = Philox word k&3 of call
+ * (block, row+offset lo, hi, 3 + 16*(k>>2)). */
 void orc_bernoulli_bitmask(uint64_t seed, uint64_t offset, int64_t M, int64_t N, double keep_prob,
                            uint32_t *bits) {
-  double th32 = keep_prob * 4294967296.0;
-  uint32_t thresh = th32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)th32;
+  enum { GB = 1024 };
+  static uint32_t T[GB + 1];
+  double qd = (1.0 - keep_prob) * 4294967296.0;
+  uint32_t q32 = qd <= 0.0 ? 0u : (qd >= 4294967295.0 ? 0xffffffffu : (uint32_t)(qd + 0.5));
+  uint64_t t = 0x100000000ull;
+  T[0] = 0xffffffffu;
+  for (int g = 1; g <= GB; ++g) { t = (t * (uint64_t)q32) >> 32; T[g] = (uint32_t)t; }
   int64_t words = (N + 31) / 32;
   memset(bits, 0, (size_t)(M * words) * sizeof(uint32_t));
-  for (int64_t i = 0; i < M; ++i)
-    for (int64_t j = 0; j < N; ++j)
-      if (lib_word(seed, offset, 3u, i, j) < thresh) bits[i * words + (j >> 5)] |= 1u << (j & 31);
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  int64_t n_blocks = (N + GB - 1) / GB;
+  for (int64_t i = 0; i < M; ++i) {
+    uint64_t r = (uint64_t)i + offset;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      int c = -1;
+      uint32_t o[4] = {0, 0, 0, 0};
+      for (int k = 0;; ++k) {
+        if ((k & 3) == 0) {
+          uint32_t ctr[4] = {(uint32_t)b, (uint32_t)r, (uint32_t)(r >> 32), 3u + ((uint32_t)(k >> 2) << 4)};
+          orc_philox4x32_10(ctr, key, o);
+        }
+        uint32_t u = o[k & 3];
+        int gap = 0;
+        for (int g = 1; g <= GB; ++g) { if (u < T[g]) gap = g; else break; }
+        c += 1 + gap;
+        if (c >= GB) break;
+        int64_t j = b * GB + c;
+        if (j >= N) break;
+        bits[i * words + (j >> 5)] |= 1u << (j & 31);
+      }
+    }
+  }
 }
 
 /* ---- cvae.py:31,39  F.normalize(W, p=2, dim=1) with eps 1e-12 ---- */

@@ -24,7 +24,8 @@ constexpr int CE_WARPS = 8;
 constexpr int CE_THREADS = CE_WARPS * 32;
 constexpr int CE_TILE_FLOATS = 8192;
 
-enum { CE_DENSE = 0, CE_BITMASK = 1, CE_PHILOX = 2 };
+enum { CE_DENSE = 0, CE_BITMASK = 1 };
+constexpr size_t CE_GB_HOST = 1024;  // == CE_GB (gap-process block, see ce_sparse_kernel)
 
 template <int D>
 struct CECfg {
@@ -69,6 +70,7 @@ static int ce_plan(const Table *t, int64_t M, CEPlan *p) {
   p->items_per_split = tps * p->tile;
   p->rec = 3 + t->dim;
   p->ws_bytes = (size_t)ns * (size_t)M * p->rec * sizeof(float);
+  if (p->ws_bytes < (CE_GB_HOST + 1) * sizeof(uint32_t)) p->ws_bytes = (CE_GB_HOST + 1) * sizeof(uint32_t);
   return PCV_OK;
 }
 
@@ -78,19 +80,6 @@ __device__ __forceinline__ void ce_cp_async16(void *smem, const void *gmem, bool
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
 }
 
-// Bernoulli(keep) draw for (row, global column j): 32-bit Philox word < thresh.
-// Same 128-column block mapping as the exponential race (4 columns per call).
-__device__ __forceinline__ bool bern_philox(uint64_t seed, uint64_t offset, int64_t row,
-                                            int64_t jglobal, uint32_t thresh) {
-  int64_t call = ((jglobal >> 7) << 5) + (jglobal & 31);
-  int e = (int)((jglobal >> 5) & 3);
-  uint64_t r = (uint64_t)row + offset;
-  Philox4 p = philox4x32_10((uint32_t)call, (uint32_t)r, (uint32_t)(r >> 32), PCV_STREAM_BERNOULLI,
-                            (uint32_t)seed, (uint32_t)(seed >> 32));
-  uint32_t w = e == 0 ? p.x : (e == 1 ? p.y : (e == 2 ? p.z : p.w));
-  return w < thresh;
-}
-
 template <int D, int MODE>
 __global__ void __launch_bounds__(CE_THREADS, 2)
 ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
@@ -98,7 +87,6 @@ ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
           int64_t items_per_split, const uint32_t *__restrict__ bitmask, int64_t mask_words,
           uint64_t seed, uint64_t offset, const uint64_t *__restrict__ offset_dev, uint32_t thresh,
           float *__restrict__ part) {
-  if (MODE == CE_PHILOX && offset_dev) offset += *offset_dev;
   using Cfg = CECfg<D>;
   constexpr int R = Cfg::R, TILE = Cfg::TILE, C4 = Cfg::C4, REC = 3 + D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,12 +154,10 @@ ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
         bool b;
         if (MODE == CE_DENSE) {
           b = true;
-        } else if (MODE == CE_BITMASK) {
+        } else {
           // base and i-lane are multiples of 32: the warp shares one word per row
           uint32_t word = (row0 + r < M) ? __ldg(bitmask + (row0 + r) * mask_words + (j >> 5)) : 0u;
           b = (word >> (j & 31)) & 1u;
-        } else {
-          b = bern_philox(seed, offset, row0 + r, j + row_offset, thresh);
         }
         b = b || (j == tgt[r]);
         in[r] = b;
@@ -274,6 +260,149 @@ __global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Sparse masked CE (keep_prob < 1, Philox mode): the Bernoulli(keep) mask of
+// train_generative.py:39 is generated as a GAP PROCESS — inside every block of
+// CE_GB consecutive columns the distance to the next kept column is Geometric(keep)
+// (memoryless, so the columns are exactly i.i.d. Bernoulli(keep)) — and only the
+// kept columns (~keep*N per row, 1000 of 100k by default) are ever touched:
+// gather the 32-byte row, exact FMA-chain logit, online soft-max, dq accumulate.
+// Work per row is O(n_neg) instead of O(N).  Gaps come from an integer inverse-CDF
+// table T[g] = floor((1-keep)^g * 2^32) built by an exact 64-bit recurrence, so the
+// mask is reproduced bit for bit by the CPU oracle (no transcendental involved).
+// One warp per row; lane = gap-process block (round-robin).
+// ---------------------------------------------------------------------------
+constexpr int CE_GB = 1024;   // columns per gap-process block
+
+__global__ void ce_gap_table_kernel(uint32_t q32, uint32_t *__restrict__ T) {
+  // T[g] = P(gap >= g) * 2^32 for g = 1..CE_GB; q32 = round((1 - keep) * 2^32); T[0] unused (= 2^32)
+  unsigned long long t = 0x100000000ull;
+  T[0] = 0xffffffffu;
+  for (int g = 1; g <= CE_GB; ++g) {
+    t = (t * (unsigned long long)q32) >> 32;
+    T[g] = (uint32_t)t;
+  }
+}
+
+// number of g in [1, CE_GB] with u < T[g]  (T is non-increasing) == the gap length, CE_GB = "past the block"
+__device__ __forceinline__ int gap_from_u(const uint32_t *__restrict__ T, uint32_t u) {
+  int lo = 0, hi = CE_GB;       // invariant: u < T[g] for all 1 <= g <= lo ; u >= T[g] for g > hi
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (u < __ldg(T + mid)) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+ce_sparse_kernel(const float *__restrict__ W, int64_t n_rows, const float *__restrict__ Q,
+                 const int64_t *__restrict__ targets, int64_t M, const uint32_t *__restrict__ T, uint64_t seed,
+                 uint64_t offset, const uint64_t *__restrict__ offset_dev, float *__restrict__ loss_rows,
+                 float *__restrict__ lse_out, float *__restrict__ dq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  if (offset_dev) offset += *offset_dev;
+  const uint64_t rr = (uint64_t)row + offset;
+  float q[D];
+#pragma unroll
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(Q + row * D) + c);
+    q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+  }
+  const int64_t tgt = targets[row];
+  float m = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) acc[k] = 0.f;
+  int cnt = 0;
+  bool seen_tgt = false;
+  auto visit = [&](int64_t j) {
+    float w[D];
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(W + j * D) + c);
+      w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s = fmaf(q[k], w[k], s);
+    ++cnt;
+    if (s > m) {
+      const float sc = __expf(m - s);
+      l *= sc;
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc[k] *= sc;
+      m = s;
+    }
+    const float p = __expf(s - m);
+    l += p;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = fmaf(p, w[k], acc[k]);
+  };
+  const int64_t n_blocks = (n_rows + CE_GB - 1) / CE_GB;
+  for (int64_t b = lane; b < n_blocks; b += 32) {
+    int c = -1;
+    Philox4 ph = {0, 0, 0, 0};
+    for (int k = 0;; ++k) {
+      if ((k & 3) == 0)
+        ph = philox4x32_10((uint32_t)b, (uint32_t)rr, (uint32_t)(rr >> 32),
+                           PCV_STREAM_BERNOULLI + ((uint32_t)(k >> 2) << 4), (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t u = (k & 3) == 0 ? ph.x : ((k & 3) == 1 ? ph.y : ((k & 3) == 2 ? ph.z : ph.w));
+      c += 1 + gap_from_u(T, u);
+      if (c >= CE_GB) break;
+      const int64_t j = b * CE_GB + c;
+      if (j >= n_rows) break;
+      if (j == tgt) seen_tgt = true;
+      visit(j);
+    }
+  }
+  // the target column is always part of the mask (train_generative.py:38)
+  const bool any_seen = __any_sync(0xffffffffu, seen_tgt);
+  if (lane == 0 && !any_seen) visit(tgt);
+  // merge the 32 lane states
+  const float mw = warp_max(m);
+  const float sc = (m == -INFINITY) ? 0.f : __expf(m - mw);
+  float lw = warp_sum(l * sc);
+  int cw = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
+  float a[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) a[k] = warp_sum(acc[k] * sc);
+  if (lane == 0) {
+    const int64_t n_out = n_rows - cw;          // masked-out logits are exactly 0
+    const float mx = n_out > 0 ? fmaxf(mw, 0.f) : mw;
+    const float resc = __expf(mw - mx);
+    const float L = lw * resc + (float)n_out * __expf(-mx);
+    const float lse = mx + logf(L);
+    const float *wt = W + tgt * D;
+    float xt = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) xt = fmaf(q[k], wt[k], xt);
+    if (loss_rows) loss_rows[row] = lse - xt;
+    if (lse_out) lse_out[row] = lse;
+    if (dq) {
+      const float inv = resc / L;
+#pragma unroll
+      for (int k = 0; k < D; ++k) dq[row * D + k] = a[k] * inv - wt[k];
+    }
+  }
+}
+
+template <int D>
+static int launch_ce_sparse(const Table *t, const float *Q, const int64_t *targets, int64_t M, const pcv_ce_mask *mask,
+                            uint32_t *T, float *loss_rows, float *lse, float *dq, cudaStream_t st) {
+  double qd = (1.0 - mask->keep_prob) * 4294967296.0;
+  const uint32_t q32 = qd <= 0.0 ? 0u : (qd >= 4294967295.0 ? 0xffffffffu : (uint32_t)(qd + 0.5));
+  ce_gap_table_kernel<<<1, 1, 0, st>>>(q32, T);
+  PCV_LAUNCH_CHECK();
+  ce_sparse_kernel<D><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, Q, targets, M, T, mask->seed,
+                                                            mask->offset, mask->offset_dev, loss_rows, lse, dq);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
 template <int D, int MODE>
 static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
                      int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
@@ -356,10 +485,17 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
   } else if (mask->keep_prob >= 1.0) {
     rc = ce_dispatch<CE_DENSE>(t, p, Q, targets, M, nullptr, 0, 0, 0, nullptr, 0, part, st);
   } else {
-    double th32 = mask->keep_prob * 4294967296.0;
-    uint32_t thresh = th32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)th32;
-    rc = ce_dispatch<CE_PHILOX>(t, p, Q, targets, M, nullptr, 0, mask->seed, mask->offset, mask->offset_dev,
-                                thresh, part, st);
+    // sparse path: only the kept columns are visited; the workspace holds the gap table
+    uint32_t *T = reinterpret_cast<uint32_t *>(workspace);
+    switch (t->dim) {
+      case 4: return launch_ce_sparse<4>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+      case 8: return launch_ce_sparse<8>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+      case 16: return launch_ce_sparse<16>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+      case 32: return launch_ce_sparse<32>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+      case 64: return launch_ce_sparse<64>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+    }
+    set_error("ce: dim %d unsupported", t->dim);
+    return PCV_ERR_UNSUPPORTED;
   }
   if (rc != PCV_OK) return rc;
   ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(
