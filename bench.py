@@ -253,7 +253,7 @@ def run_train(args, w):
     model, _ = build_gpu(w, sd, env_sd, "greedy", device)
     model.noise.reseed(99 + rank)
     n_neg = w["n_items"] if args.n_neg <= 0 else args.n_neg
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=(world == 1))
     params = [p for p in model.parameters() if p.requires_grad]
     batches = [make_train_batch(w, B, i, seed=4321 + 7919 * rank) for i in range(K + W)]
     dev_batches = [{k: v.to(device) for k, v in b.items()} for b in batches]
@@ -283,33 +283,52 @@ def run_train(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if world == 1:     # single GPU: the whole step is one CUDA graph (the DP arm keeps the eager NCCL all-reduce)
+        from pivotcvae_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, B, 0.001, n_neg)
+        run = lambda b: graphed(b)[0]
+    else:
+        run = step
     for i in range(W):
-        step(dev_batches[i])
+        run(dev_batches[i])
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = ops.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    with ops.KernelTimer() as kt:
-        for i in range(K):
-            flush.zero_()
-            ev[i][0].record()
-            step(dev_batches[W + i])
-            ev[i][1].record()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        run(dev_batches[W + i])
+        ev[i][1].record()
     barrier()
-    launches = ops.launch_count() - l0
+    launches = graphed.launches_per_step * K if graphed else ops.launch_count() - l0
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    ksum = kt.summary()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for i in range(K):
         flush.zero_()
         ev2[i][0].record()
-        b = {k: v.to(device, non_blocking=True) for k, v in pin_batches[W + i].items()}
-        loss = step(b)
+        if graphed:
+            loss = run(pin_batches[W + i])
+        else:
+            loss = run({k: v.to(device, non_blocking=True) for k, v in pin_batches[W + i].items()})
         loss_h.copy_(loss.detach(), non_blocking=True)
         ev2[i][1].record()
     barrier()
+    # per-kernel CUDA-event timing of the same step launched eagerly (roofline of the dominant kernel)
+    with ops.KernelTimer() as kt:
+        for i in range(min(K, 10)):
+            flush.zero_()
+            if graphed:
+                for k_, v_ in graphed.static.items():
+                    v_.copy_(dev_batches[W + i][k_].reshape(v_.shape))
+                graphed._step()
+            else:
+                step(dev_batches[W + i])
+    barrier()
+    ksum = kt.summary()
     clk = clocks.stop() if rank == 0 else None
     ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)

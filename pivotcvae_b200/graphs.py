@@ -51,3 +51,47 @@ class GraphedSlateGenerator:
         """-> (items int64[B*L], resp f32[B, L]) in static buffers (overwritten by the next call)."""
         self.load_inputs(ctx, users)
         return self.replay()
+
+
+class GraphedTrainStep:
+    """One training step (get_gen_loss -> backward -> Adam.step, train_generative.py:124-134)
+    captured as ONE CUDA graph over static batch buffers.  The optimizer must be built with
+    capturable=True.  Philox masks / eps stay fresh per replay (device-side counter)."""
+
+    def __init__(self, model, optimizer, batch, beta, n_neg, warmup=3):
+        from .train_generative import get_gen_loss
+        dev = model.docEmbed.weight.device
+        L = model.slate_size
+        self.model, self.opt = model, optimizer
+        self.static = {"slates": torch.zeros(batch, L, dtype=torch.int64, device=dev),
+                       "users": torch.zeros(batch, 1, dtype=torch.int64, device=dev),
+                       "responses": torch.zeros(batch, L, device=dev)}
+
+        def step():
+            optimizer.zero_grad(set_to_none=True)
+            loss, rec, kld = get_gen_loss(self.static, model, None, beta, n_neg=n_neg)
+            loss.backward()
+            optimizer.step()
+            model.noise.end_graph_step()
+            return loss.detach(), rec.detach(), kld.detach()
+
+        self._step = step
+        model.noise.begin_graph(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.rec, self.kld = step()
+        self.launches_per_step = ops.launch_count() - l0
+
+    def __call__(self, batch):
+        for k, v in self.static.items():
+            v.copy_(batch[k].reshape(v.shape), non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.rec, self.kld
