@@ -382,13 +382,16 @@ def run_ours(args, w):
     B, K, W = (args.batch or w["B"]), args.steps, args.warmup
     sd, env_sd = make_weights(w, "list" if mode == "list" else "pivot")
     model, env = build_gpu(w, sd, env_sd, mode, device)
-    model.noise.reseed(1234 + rank)
+    vp = args.parallel == "vp" and world > 1
+    model.noise.reseed(1234 + (0 if vp else rank))   # vocab-parallel ranks replicate inputs AND noise
     model.select_engine = args.engine
+    if vp:
+        model.enable_vocab_parallel()
     no_user = w["no_user"]
 
     # synthetic inputs: one distinct batch per step, resident in HBM for `value`
     n_in = K + W
-    ctxs, userss = zip(*[make_inputs(w, B, i, seed=1234 + 7919 * rank) for i in range(n_in)])
+    ctxs, userss = zip(*[make_inputs(w, B, i, seed=1234 + (0 if vp else 7919 * rank)) for i in range(n_in)])
     ctx_d = [c.to(device) for c in ctxs]
     usr_d = [u.to(device) for u in userss]
     ctx_h = [c.pin_memory() for c in ctxs]
@@ -406,7 +409,34 @@ def run_ours(args, w):
 
     # the whole step (recommend + response score) is one CUDA graph over static buffers;
     # the Philox row counter lives on the device, so every replay draws fresh noise
-    gen = GraphedSlateGenerator(model, env, B, warmup=3)
+    if vp:
+        # vocab-parallel: the per-step NCCL all-gathers stay eager (not captured)
+        class _Eager:
+            launches_per_step = 0
+
+            def __init__(self):
+                self.ctx = torch.zeros(B, w["L"], device=device)
+                self.users = torch.zeros(B, dtype=torch.int64, device=device)
+
+            def load_inputs(self, c, u=None):
+                self.ctx.copy_(c, non_blocking=True)
+                if u is not None:
+                    self.users.copy_(u, non_blocking=True)
+
+            def _step(self):
+                items, _ = model.recommend(self.ctx, None if no_user else self.users, return_item=True)
+                return items, None, env(items.view(B, -1), self.users)
+
+            def __call__(self, c, u=None):
+                self.load_inputs(c, u)
+                l0_ = ops.launch_count()
+                items, _, resp = self._step()
+                self.launches_per_step = ops.launch_count() - l0_
+                return items, resp
+
+        gen = _Eager()
+    else:
+        gen = GraphedSlateGenerator(model, env, B, warmup=3)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -459,11 +489,13 @@ def run_ours(args, w):
             dist.destroy_process_group()
         return
 
-    total = B * world * K
+    total = B * (1 if vp else world) * K      # vocab-parallel: all ranks work on the SAME batch (strong scaling)
     value = total / (ms / 1e3)
     e2e = total / (ms_e2e / 1e3)
     # ---- roofline of the dominant kernel: the per-slot score+select over the catalog
     L_, D, N = w["L"], w["D"], w["n_items"]
+    if vp:
+        N = model.item_table().n_rows      # the local shard this rank scores
     key = "score_select_greedy_M%d" % (B * L_)
     dom = ksum.get(key, {"ms_avg": float("nan"), "calls": 0})
     peaks = {}
@@ -489,11 +521,13 @@ def run_ours(args, w):
         cpu = {"value": cb / sec, "unit": "slates/s", "cores": threads, "kind": "port",
                "sample": "%d steps of %d slates of the same workload (oracle/pcv_oracle.c, pthreads x%d)" % (n, cb, threads)}
     line = {"metric": "generated slates/sec (%s)" % mode, "value": value, "unit": "slates/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if vp else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "batch_per_gpu": B, "mode": mode, "parallelism": "dp%d (replicated table)" % world,
+            "config": {"workload": w["desc"], "batch_per_gpu": B, "mode": mode,
+                       "parallelism": ("vp%d (catalog sharded, 1 all-gather per scoring step)" % world) if vp else "dp%d (replicated table)" % world,
                        "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed",
-                       "launch": "one CUDA graph replay per step (%d kernels of libpcv_b200)" % gen.launches_per_step},
+                       "launch": ("eager launches + NCCL all-gathers (%d kernels of libpcv_b200 per step)" if vp else
+                                  "one CUDA graph replay per step (%d kernels of libpcv_b200)") % gen.launches_per_step},
             "e2e": {"value": e2e, "unit": "slates/s", "h2d_bytes_per_step": int(B * w["L"] * 4 + B * 8),
                     "d2h_bytes_per_step": int(B * w["L"] * 8 + B * w["L"] * 4), "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
@@ -513,6 +547,7 @@ def main():
     ap.add_argument("--n-neg", type=int, default=0, help="train mode: negatives per row (0 = the whole catalog)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--parallel", default="dp", choices=["dp", "vp"], help="N>1: batch data-parallel (default) or vocab-parallel")
     ap.add_argument("--cpu-batch", type=int, default=256, help="slates per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

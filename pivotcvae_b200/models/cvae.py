@@ -46,12 +46,35 @@ class BaseCVAE(nn.Module):
         self.noise = NoiseSource()
         self.select_engine = "auto"
         self._table = None
+        self._vp = None      # vocab-parallel state: (group, lo, hi) once enable_vocab_parallel() is called
 
     # ---- extension state is rebuilt lazily (whole-model pickling, train_generative.py:199)
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_table"] = None
+        st["_vp"] = None
         return st
+
+    # ---- vocab-parallel scoring: every rank keeps the full fp32 table (<= 320 MB) for the
+    # gathers, but scores only its own 128-aligned row shard; one all-gather of (val, idx) per scoring step
+    def enable_vocab_parallel(self, group=None):
+        import torch.distributed as dist
+        from ..parallel import shard_bounds
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        lo, hi = shard_bounds(self.docEmbed.weight.shape[0], world, rank)
+        self._vp = (group, lo, hi)
+        self._table = None
+
+    def _select(self, q, mode="greedy", **kw):
+        """score+select over the (possibly sharded) catalog -> global item ids int64 (rows,)."""
+        if self._vp is None:
+            return ops.score_select(self.item_table(), q, mode, engine=self.select_engine if mode == "greedy" else "auto",
+                                    want_val=False, **kw)[0]
+        from ..parallel import VocabParallelSelector
+        group = self._vp[0]
+        local = lambda x: ops.score_select(self.item_table(), x, mode,
+                                           engine=self.select_engine if mode == "greedy" else "auto", **kw)
+        return VocabParallelSelector(local, group)(q)[0]
 
     def _apply(self, fn, *a, **k):
         self._table = None
@@ -60,6 +83,12 @@ class BaseCVAE(nn.Module):
     def item_table(self):
         w = self.docEmbed.weight
         t = self._table
+        if self._vp is not None:
+            _, lo, hi = self._vp
+            if t is None or t.row_offset != lo or t.n_rows != hi - lo or t.weight.data_ptr() != w[lo:hi].data_ptr():
+                t = ops.Table(w.detach()[lo:hi], row_offset=lo)
+                self._table = t
+            return t
         if t is None or t.weight.data_ptr() != w.data_ptr() or t.n_rows != w.shape[0]:
             t = ops.Table(w.detach())
             self._table = t
@@ -133,8 +162,7 @@ class BaseCVAE(nn.Module):
     def get_recommended_item(self, embeddings):
         """arg-max item per row over the whole catalog (cvae.py:97-101) -> int64 (rows,)."""
         q = embeddings.reshape(-1, self.feature_size)
-        idx, _ = ops.score_select(self.item_table(), q.detach(), "greedy", engine=self.select_engine, want_val=False)
-        return idx
+        return self._select(q.detach(), "greedy")
 
     def sample_encoding(self, s, r, u=None):
         """encoder only (cvae.py:103-115) -> (z_mu, z_logvar)."""

@@ -60,12 +60,14 @@ class UserPivotCVAE(BaseCVAE):
             q = self.docEmbed.weight[true_pivot.to(self._dev(), torch.int64).reshape(-1)]
         q = q.detach()
         if how == "max":
-            return ops.score_select(self.item_table(), q, "greedy", engine=self.select_engine, want_val=False)[0]
+            return self._select(q, "greedy")
         noise = self.noise.pop("race")
         if noise is not None:
-            return ops.score_select(self.item_table(), q, "exprace", noise=noise.to(self._dev()), want_val=False)[0]
-        return ops.score_select(self.item_table(), q, "exprace", want_val=False,
-                                **self.noise.stream_args(q.shape[0]))[0]
+            noise = noise.to(self._dev())
+            if self._vp is not None:      # external noise is [B, N]: every shard reads its own columns
+                noise = noise[:, self._vp[1]:self._vp[2]].contiguous()
+            return self._select(q, "exprace", noise=noise)
+        return self._select(q, "exprace", **self.noise.stream_args(q.shape[0]))
 
     def pick_pivot(self, pivot_output, true_pivot=[]):
         return self.docEmbed.weight[self._pick_index(pivot_output, true_pivot)]

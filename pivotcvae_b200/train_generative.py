@@ -43,6 +43,9 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
     if model.candidateFlag:
         raise NotImplementedError("candidate-mode training is SURVEY §8(f) N1: not built yet (use --mask_train)")
     rx, z, mu, logvar, _ = model.forward_latent(slates, targets, users)
+    if getattr(model, "_vp", None) is not None:
+        raise NotImplementedError("vocab-parallel training (CE partials + dQ all-reduce) is not built yet; "
+                                  "train data-parallel with the replicated table")
     table = model.item_table()
     N = table.n_rows
     if n_neg > N:
