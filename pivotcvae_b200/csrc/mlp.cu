@@ -57,18 +57,22 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t offset, int64_t 
   n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
 }
 
-// Thread mapping: 256 threads = (256/CT column groups) x (CT row groups of 8 rows);
-// a thread owns CT adjacent output columns x 8 batch rows, BM = 8*CT rows per CTA.
+// Thread mapping: THREADS = (256/CT column groups) x (row groups of RT rows); a thread owns
+// CT adjacent output columns x RT batch rows.  Small batches use <CT=1, RT=4, 512 threads>
+// (8 rows per CTA, 16 warps per SM to hide the shared-memory latency); larger ones
+// <CT=2|4, RT=8, 256 threads> (16 / 32 rows per CTA).
 // Activations live TRANSPOSED in shared memory (actT[k][row]) so a thread's 8 rows
 // are two broadcast LDS.128; the weight stage wst[kk][n] is read conflict-free.
 // Weight chunks are prefetched into registers one chunk ahead (across column blocks
 // and layers) and double-buffered in shared memory: one __syncthreads per chunk.
-template <int CT>
-__global__ void __launch_bounds__(MLP_THREADS)
+template <int CT, int RT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 mlp_fwd_kernel(const MlpParams P, int64_t B) {
-  constexpr int BM = 8 * CT;
-  constexpr int CG = MLP_NB / CT;   // column groups (threads along n)
-  constexpr int ALD = BM + 4;       // actT row stride (floats)
+  constexpr int CG = MLP_NB / CT;          // column groups (threads along n)
+  constexpr int BM = RT * (THREADS / CG);  // batch rows per CTA
+  constexpr int ALD = BM + 4;              // actT row stride (floats)
+  constexpr int KSPLIT = THREADS / MLP_NB; // threads sharing the staging of one weight column
+  constexpr int KPT = MLP_KC / KSPLIT;     // k values staged per thread and chunk
   extern __shared__ __align__(16) float smem[];
   const int ld = P.ld;              // max width (multiple of 4)
   float *actA = smem;               // [ld][ALD]
@@ -82,21 +86,23 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
 
   // ---------------- weight-chunk stream (layer, column block, k-chunk) ----------------
   int pl = 0, pnb = 0, pkc = 0;     // position of the chunk held in wv
-  float wv[MLP_KC];
+  float wv[KPT];
+  const int sn = tid % MLP_NB;              // weight column this thread stages
+  const int sk = (tid / MLP_NB) * KPT;      // first k (within the chunk) it stages
   auto fetch = [&](int l, int nb, int kc) {
     const int K = d.layer[l].n_in, NO = d.layer[l].n_out;
-    const int n = nb + tid;
+    const int n = nb + sn;
     if (n < NO) {
-      const float *wrow = d.layer[l].W + (int64_t)n * K + kc;
+      const float *wrow = d.layer[l].W + (int64_t)n * K + kc + sk;
       if (kc + MLP_KC <= K && ((K & 3) == 0)) {
 #pragma unroll
-        for (int v = 0; v < MLP_KC / 4; ++v) {
+        for (int v = 0; v < KPT / 4; ++v) {
           const float4 t4 = __ldg(reinterpret_cast<const float4 *>(wrow) + v);
           wv[4 * v] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
         }
       } else {
 #pragma unroll
-        for (int kk = 0; kk < MLP_KC; ++kk) wv[kk] = (kc + kk < K) ? __ldg(wrow + kk) : 0.f;
+        for (int kk = 0; kk < KPT; ++kk) wv[kk] = (kc + sk + kk < K) ? __ldg(wrow + kk) : 0.f;
       }
     }
   };
@@ -113,7 +119,7 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
 
   // ---------------- prologue: assemble x0 into actA (transposed) ----------------
   {
-    constexpr int TPR = MLP_THREADS / BM;  // threads per row
+    constexpr int TPR = THREADS / BM;  // threads per row
     const int row = tid / TPR, sub = tid % TPR;
     const int64_t b = b0 + row;
     float *x = actA + row;                 // element e at x[e * ALD]
@@ -178,17 +184,17 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
     const bool last = (l == d.n_layers - 1);
     const int K = L.n_in;
     for (int nb = 0; nb < L.n_out; nb += MLP_NB) {
-      float acc[8][CT];
+      float acc[RT][CT];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
 
       for (int kc = 0; kc < K; kc += MLP_KC) {
         float *ws = wst + buf * (MLP_KC * MLP_WLD);
-        if (nb + tid < L.n_out) {   // narrow layers: only the threads that own a real column stage it
+        if (nb + sn < L.n_out) {   // narrow layers: only the threads that own a real column stage it
 #pragma unroll
-          for (int kk = 0; kk < MLP_KC; ++kk) ws[kk * MLP_WLD + tid] = wv[kk];
+          for (int kk = 0; kk < KPT; ++kk) ws[(sk + kk) * MLP_WLD + sn] = wv[kk];
         }
         __syncthreads();
         if (more) {
@@ -196,10 +202,14 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
           if (more) fetch(pl, pnb, pkc);   // next chunk's loads fly during this chunk's FMAs
         }
         const int kmax = (nb + cg * CT < L.n_out) ? min(MLP_KC, K - kc) : 0;   // idle column groups skip the FMAs
-        const float *ap = cur + (size_t)kc * ALD + rg * 8;
+        const float *ap = cur + (size_t)kc * ALD + rg * RT;
         auto fma_step = [&](int kk) {
-          const float4 a0 = *reinterpret_cast<const float4 *>(ap + kk * ALD);
-          const float4 a1 = *reinterpret_cast<const float4 *>(ap + kk * ALD + 4);
+          float a[RT];
+#pragma unroll
+          for (int v = 0; v < RT / 4; ++v) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(ap + kk * ALD + 4 * v);
+            a[4 * v] = t4.x; a[4 * v + 1] = t4.y; a[4 * v + 2] = t4.z; a[4 * v + 3] = t4.w;
+          }
           float w[CT];
           if (CT == 4) {
             const float4 t4 = *reinterpret_cast<const float4 *>(ws + kk * MLP_WLD + cg * 4);
@@ -210,9 +220,8 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
           } else {
             w[0] = ws[kk * MLP_WLD + cg];
           }
-          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+          for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
         };
@@ -231,15 +240,16 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
         const int n = nb + cg * CT + c;
         if (n < L.n_out) {
           const float bias = __ldg(L.b + n);
-          float v[8];
+          float v[RT];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) v[r] = apply_act(acc[r][c] + bias, L.act);
-          float *np = nxt + (size_t)n * ALD + rg * 8;
-          *reinterpret_cast<float4 *>(np) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4 *>(np + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          for (int r = 0; r < RT; ++r) v[r] = apply_act(acc[r][c] + bias, L.act);
+          float *np = nxt + (size_t)n * ALD + rg * RT;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int64_t b = b0 + rg * 8 + r;
+          for (int q4 = 0; q4 < RT / 4; ++q4)
+            *reinterpret_cast<float4 *>(np + 4 * q4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            const int64_t b = b0 + rg * RT + r;
             if (b < B) {
               if (last) d.out[b * d.out_ld + d.out_col0 + n] = v[r];
               else if (d.acts[l]) d.acts[l][b * L.n_out + n] = v[r];
@@ -256,7 +266,7 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
   if (d.latent > 0) {
     const int Z = d.latent;
     const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
-    for (int e = tid; e < BM * Z; e += MLP_THREADS) {
+    for (int e = tid; e < BM * Z; e += THREADS) {
       const int row = e / Z, j = e - row * Z;
       const int64_t b = b0 + row;
       if (b >= B) continue;
@@ -369,21 +379,21 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs
+  // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs (and use 16 warps per CTA)
   const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
   const int BM = 8 * CT;
   size_t smem = (size_t)(2 * P.ld * (BM + 4) + 2 * MLP_KC * MLP_WLD) * sizeof(float);
   int64_t blocks = (B + BM - 1) / BM;
   cudaStream_t st = (cudaStream_t)stream;
   if (CT == 1) {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<1><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<1, 4, 512><<<(unsigned)blocks, 512, smem, st>>>(P, B);
   } else if (CT == 2) {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<2><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<2, 8, 256><<<(unsigned)blocks, 256, smem, st>>>(P, B);
   } else {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<4><<<(unsigned)blocks, MLP_THREADS, smem, st>>>(P, B);
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_fwd_kernel<4, 8, 256><<<(unsigned)blocks, 256, smem, st>>>(P, B);
   }
   PCV_LAUNCH_CHECK();
   return PCV_OK;
