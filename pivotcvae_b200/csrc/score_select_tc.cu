@@ -494,10 +494,14 @@ struct TcPlan {
   int row_tiles, n_split;
   unsigned int ovf_cap;
   int64_t items_per_split;
+  int64_t rows_per_launch;   // rows handled per kernel triple; larger M is processed in groups
   size_t ws_bytes;
 };
 
-static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
+constexpr size_t TC_WS_CAP = 192ull << 20;   // workspace budget: bigger problems are split into row groups
+
+static void tc_plan_rows(const Table *t, int64_t M, TcPlan *p) {
+  p->rows_per_launch = M;
   p->row_tiles = (int)((M + TC_BM - 1) / TC_BM);
   const int64_t tiles = (t->n_rows + TC_BN - 1) / TC_BN;
   int64_t max_split = tiles / 8;  // keep >= 8 tiles per CTA to amortise the prologue
@@ -521,6 +525,15 @@ static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
   const size_t n_sr = (size_t)TC_SLICES * p->n_split * (size_t)M;
   p->ovf_cap = (unsigned int)(n_sr / 16 < 65536 ? 65536 : (n_sr / 16 > (1u << 24) ? (1u << 24) : n_sr / 16));
   p->ws_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)M * 8 + (size_t)p->ovf_cap * 12 + 256;
+}
+
+static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
+  int64_t mc = M;
+  tc_plan_rows(t, mc, p);
+  while (p->ws_bytes > TC_WS_CAP && mc > TC_BM) {   // halve the row group until the workspace fits the budget
+    mc = ((mc + 1) / 2 + TC_BM - 1) / TC_BM * TC_BM;
+    tc_plan_rows(t, mc, p);
+  }
 }
 
 bool score_select_tc_supported(const Table *t) { return t->dim == TC_D && t->tmap_valid; }
@@ -581,16 +594,15 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     set_error("score_select(tcgen05): workspace too small (%zu < %zu)", ws_bytes, p.ws_bytes);
     return PCV_ERR_WORKSPACE;
   }
-  const size_t n_sr = (size_t)TC_SLICES * p.n_split * (size_t)M;   // (stream, row) pairs
+  const int64_t Mg = p.rows_per_launch;                                // rows per group (== M when it fits)
+  const size_t n_sr = (size_t)TC_SLICES * p.n_split * (size_t)Mg;      // (stream, row) pairs of one group
   unsigned long long *ent = reinterpret_cast<unsigned long long *>(ws);
-  unsigned long long *row_best = ent + n_sr * TC_OUT;                  // [M]   zeroed below
-  unsigned long long *ovf_ent = row_best + M;                          // [ovf_cap]
+  unsigned long long *row_best = ent + n_sr * TC_OUT;                  // [Mg]   zeroed below
+  unsigned long long *ovf_ent = row_best + Mg;                         // [ovf_cap]
   unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ovf_ent + p.ovf_cap);  // [2] zeroed below (counter + pad)
   float *rr = reinterpret_cast<float *>(ovf_count + 2);
   int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);
   int32_t *ovf_row = cc + n_sr;
-  PCV_CUDA(cudaMemsetAsync(row_best, 0, (size_t)M * 8, st));
-  PCV_CUDA(cudaMemsetAsync(ovf_count, 0, 8, st));
   const size_t smem = sizeof(TcSmem) + 1024;
   static bool attr_set[64] = {false};
   if (!attr_set[t->device & 63]) {
@@ -599,17 +611,24 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
   }
   // |tf32 chain - fp32 chain| <= 1.25 * 2^-9 * |q| * max|w|; the band is twice that
   const float band_scale = 2.0f * 1.25f * 0.001953125f * t->max_row_norm;
-  dim3 grid((unsigned)p.row_tiles, (unsigned)p.n_split);
-  score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Q, M, p.items_per_split,
-                                                         band_scale, rr, cc, ent, ovf_count, ovf_ent, ovf_row,
-                                                         p.ovf_cap);
-  PCV_LAUNCH_CHECK();
-  tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Q, ovf_count, ovf_ent, ovf_row, p.ovf_cap, row_best);
-  PCV_LAUNCH_CHECK();
-  tc_refine_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Q, M, p.n_split,
-                                                           p.items_per_split, band_scale, rr, cc, ent, row_best,
-                                                           out_idx, out_val);
-  PCV_LAUNCH_CHECK();
+  for (int64_t r0 = 0; r0 < M; r0 += Mg) {   // row groups reuse the workspace back to back on the stream
+    const int64_t m = (M - r0 < Mg) ? (M - r0) : Mg;
+    const float *Qg = Q + r0 * TC_D;
+    PCV_CUDA(cudaMemsetAsync(row_best, 0, (size_t)m * 8, st));
+    PCV_CUDA(cudaMemsetAsync(ovf_count, 0, 8, st));
+    dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)p.n_split);
+    score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, p.items_per_split,
+                                                           band_scale, rr, cc, ent, ovf_count, ovf_ent, ovf_row,
+                                                           p.ovf_cap);
+    PCV_LAUNCH_CHECK();
+    tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Qg, ovf_count, ovf_ent, ovf_row, p.ovf_cap,
+                                                    row_best);
+    PCV_LAUNCH_CHECK();
+    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, p.n_split,
+                                                             p.items_per_split, band_scale, rr, cc, ent, row_best,
+                                                             out_idx + r0, out_val ? out_val + r0 : nullptr);
+    PCV_LAUNCH_CHECK();
+  }
   return PCV_OK;
 }
 

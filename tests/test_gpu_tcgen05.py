@@ -122,3 +122,21 @@ def test_tc_full_size_properties(ops):
     assert torch.equal(mi, idx) and torch.equal(mv, val)
     si, sv = ops.score_select(full, Q[:2048], "greedy", engine="simt")
     assert torch.equal(si, idx[:2048]) and torch.equal(sv, val[:2048])
+
+
+def test_tc_row_groups_and_max_size(ops):
+    """M large enough that the workspace budget forces several row groups (C5-style: 10 M items)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_items, M = 10_000_000, 16384
+    W = torch.nn.functional.normalize(torch.randn(n_items, 8, generator=g, device="cuda"), dim=1)
+    Q = torch.randn(M, 8, generator=g, device="cuda")
+    plant = torch.randint(0, n_items, (M,), generator=g, device="cuda")
+    Q[::7] = 1.5 * W[plant[::7]]
+    tab = ops.Table(W)
+    assert tab.workspace("select", M).numel() <= (200 << 20)
+    idx, val = ops.score_select(tab, Q, "greedy", engine="tcgen05")
+    assert torch.equal(W[idx[::7]], W[plant[::7]])
+    exact = (W[idx] * Q).sum(-1)
+    assert bool(((exact - val).abs() <= 1e-5).all())
+    si, sv = ops.score_select(tab, Q[:512], "greedy", engine="simt")
+    assert torch.equal(si, idx[:512]) and torch.equal(sv, val[:512])
