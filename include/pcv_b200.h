@@ -172,6 +172,9 @@ typedef struct {
 } pcv_mlp_desc;
 
 int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream);
+/* Two chained blocks in ONE launch: b may read (as DENSE segments) what a writes for the same
+ * batch rows, e.g. prior -> reparameterise -> PSM (pivotcvae.py:279-291, 204-210). */
+int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_stream_t stream);
 
 /* KL(q || p) between diagonal Gaussians, summed over batch and latent
  * (train_generative.py:61) plus analytic grads (any grad pointer may be NULL).

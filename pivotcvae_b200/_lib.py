@@ -79,6 +79,7 @@ EXPORTS = {
     "pcv_philox_exponential": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "pcv_vp_merge_select": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "pcv_mlp_fwd": (c_int, [ctypes.POINTER(MlpDesc), c_int64, c_void_p]),
+    "pcv_mlp_fwd2": (c_int, [ctypes.POINTER(MlpDesc), ctypes.POINTER(MlpDesc), c_int64, c_void_p]),
     "pcv_kl_fwd_bwd": (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 5 + [c_void_p]),
     "pcv_ce_workspace_bytes": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_size_t)]),
     "pcv_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(CeMask), c_void_p,

@@ -66,14 +66,12 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t offset, int64_t 
 // Weight chunks are prefetched into registers one chunk ahead (across column blocks
 // and layers) and double-buffered in shared memory: one __syncthreads per chunk.
 template <int CT, int RT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-mlp_fwd_kernel(const MlpParams P, int64_t B) {
+__device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *smem) {
   constexpr int CG = MLP_NB / CT;          // column groups (threads along n)
   constexpr int BM = RT * (THREADS / CG);  // batch rows per CTA
   constexpr int ALD = BM + 4;              // actT row stride (floats)
   constexpr int KSPLIT = THREADS / MLP_NB; // threads sharing the staging of one weight column
   constexpr int KPT = MLP_KC / KSPLIT;     // k values staged per thread and chunk
-  extern __shared__ __align__(16) float smem[];
   const int ld = P.ld;              // max width (multiple of 4)
   float *actA = smem;               // [ld][ALD]
   float *actB = actA + ld * ALD;
@@ -287,6 +285,29 @@ mlp_fwd_kernel(const MlpParams P, int64_t B) {
   }
 }
 
+template <int CT, int RT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mlp_fwd_kernel(const MlpParams P, int64_t B) {
+  extern __shared__ __align__(16) float smem[];
+  mlp_block<CT, RT, THREADS>(P, B, smem);
+}
+
+// Two chained blocks in one launch (e.g. prior -> reparameterise -> PSM, pivotcvae.py:279-291 +
+// 204-210): block B's prologue reads what block A just wrote for the SAME batch rows (z), so a
+// CTA-level fence + barrier is all the ordering it needs.
+struct MlpParams2 {
+  MlpParams a, b;
+};
+template <int CT, int RT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+mlp_fwd2_kernel(const MlpParams2 P, int64_t B) {
+  extern __shared__ __align__(16) float smem[];
+  mlp_block<CT, RT, THREADS>(P.a, B, smem);
+  __threadfence_block();
+  __syncthreads();
+  mlp_block<CT, RT, THREADS>(P.b, B, smem);
+}
+
 // KL(q||p) summed (train_generative.py:61) with analytic gradients; one CTA,
 // fixed reduction order (deterministic).
 __global__ void __launch_bounds__(1024)
@@ -322,13 +343,12 @@ using namespace pcv;
 
 extern "C" {
 
-int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
+static int mlp_prepare(const pcv_mlp_desc *d, MlpParams *Pp, int *maxw_out, int *bias_total) {
+  MlpParams &P = *Pp;
   PCV_CHECK_ARG(d != nullptr, "desc is NULL");
-  PCV_CHECK_ARG(B > 0, "B must be > 0");
   PCV_CHECK_ARG(d->n_segments >= 1 && d->n_segments <= PCV_MAX_SEGMENTS, "bad n_segments");
   PCV_CHECK_ARG(d->n_layers >= 1 && d->n_layers <= PCV_MAX_LAYERS, "bad n_layers");
   PCV_CHECK_ARG(d->out != nullptr, "out is NULL");
-  MlpParams P;
   P.d = *d;
   int off = 0;
   for (int s = 0; s < d->n_segments; ++s) {
@@ -352,6 +372,7 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
   P.n_in0 = off;
   int maxw = off;
   int prev = off;
+  int bt = 0;
   for (int l = 0; l < d->n_layers; ++l) {
     const pcv_linear &L = d->layer[l];
     PCV_CHECK_ARG(L.W && L.b, "layer weights are NULL");
@@ -363,6 +384,7 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
     PCV_CHECK_ARG(((uintptr_t)L.W & 15) == 0, "layer weight must be 16-byte aligned");
     if (L.n_out > maxw) maxw = L.n_out;
     prev = L.n_out;
+    bt += L.n_out;
   }
   PCV_CHECK_ARG(maxw <= PCV_MAX_WIDTH, "layer wider than PCV_MAX_WIDTH");
   PCV_CHECK_ARG(d->copy_seg < d->n_segments, "copy_seg out of range");
@@ -371,10 +393,12 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
     PCV_CHECK_ARG(prev == 2 * d->latent, "reparam needs the last layer to emit 2*latent");
     PCV_CHECK_ARG(d->z != nullptr, "z is NULL");
   }
-  int rc = check_arch();
-  if (rc != PCV_OK) return rc;
+  *maxw_out = maxw;
+  *bias_total = bt;
+  return PCV_OK;
+}
 
-  P.ld = (maxw + 3) & ~3;
+static int mlp_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaStream_t st) {
   int sm_count = 148;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -382,21 +406,51 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
   // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs (and use 16 warps per CTA)
   const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
   const int BM = 8 * CT;
-  size_t smem = (size_t)(2 * P.ld * (BM + 4) + 2 * MLP_KC * MLP_WLD) * sizeof(float);
+  const int ld = Pb ? (Pa->ld > Pb->ld ? Pa->ld : Pb->ld) : Pa->ld;
+  size_t smem = (size_t)(2 * ld * (BM + 4) + 2 * MLP_KC * MLP_WLD) * sizeof(float);
   int64_t blocks = (B + BM - 1) / BM;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (CT == 1) {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<1, 4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<1, 4, 512><<<(unsigned)blocks, 512, smem, st>>>(P, B);
-  } else if (CT == 2) {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<2, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<2, 8, 256><<<(unsigned)blocks, 256, smem, st>>>(P, B);
-  } else {
-    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<4, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_fwd_kernel<4, 8, 256><<<(unsigned)blocks, 256, smem, st>>>(P, B);
+#define PCV_MLP_LAUNCH(CTv, RTv, THv)                                                                              \
+  if (Pb) {                                                                                                        \
+    MlpParams2 P2;                                                                                                 \
+    P2.a = *Pa; P2.b = *Pb;                                                                                        \
+    P2.a.ld = ld; P2.b.ld = ld;                                                                                    \
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd2_kernel<CTv, RTv, THv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mlp_fwd2_kernel<CTv, RTv, THv><<<(unsigned)blocks, THv, smem, st>>>(P2, B);                                  \
+  } else {                                                                                                         \
+    PCV_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<CTv, RTv, THv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mlp_fwd_kernel<CTv, RTv, THv><<<(unsigned)blocks, THv, smem, st>>>(*Pa, B);                                  \
   }
+  if (CT == 1) { PCV_MLP_LAUNCH(1, 4, 512) } else if (CT == 2) { PCV_MLP_LAUNCH(2, 8, 256) } else { PCV_MLP_LAUNCH(4, 8, 256) }
+#undef PCV_MLP_LAUNCH
   PCV_LAUNCH_CHECK();
   return PCV_OK;
+}
+
+int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream) {
+  PCV_CHECK_ARG(B > 0, "B must be > 0");
+  MlpParams P;
+  int maxw = 0, bt = 0;
+  int rc = mlp_prepare(d, &P, &maxw, &bt);
+  if (rc != PCV_OK) return rc;
+  rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  P.ld = (maxw + 3) & ~3;
+  return mlp_launch(&P, nullptr, B, (cudaStream_t)stream);
+}
+
+int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_stream_t stream) {
+  PCV_CHECK_ARG(B > 0, "B must be > 0");
+  MlpParams Pa, Pb;
+  int wa = 0, wb = 0, bt = 0;
+  int rc = mlp_prepare(a, &Pa, &wa, &bt);
+  if (rc != PCV_OK) return rc;
+  rc = mlp_prepare(b, &Pb, &wb, &bt);
+  if (rc != PCV_OK) return rc;
+  rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  Pa.ld = (wa + 3) & ~3;
+  Pb.ld = (wb + 3) & ~3;
+  return mlp_launch(&Pa, &Pb, B, (cudaStream_t)stream);
 }
 
 int pcv_kl_fwd_bwd(const float *mu, const float *logvar, const float *pmu, const float *plogvar,

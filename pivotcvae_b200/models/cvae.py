@@ -207,6 +207,24 @@ class BaseCVAE(nn.Module):
             return self._run_block(segs, layers, B, latent=self.latent_size, **self._eps_args(B))
         return self._run_block(segs, layers, B), None
 
+    def _prior_chain(self, r, u, next_mods, last_act=L.ACT_NONE):
+        """Inference only: prior block (+ reparameterisation) and the block that consumes z
+        ([z, onehot(r), user] -> next_mods) in ONE kernel launch.  -> (mu|logvar, z, next block's output)"""
+        B = r.shape[0]
+        cond = ops.OneHot(r)
+        user = [] if self.noUser else [ops.Gather(self.userEmbed.weight.detach(), u.reshape(-1, 1))]
+        layers = [(w.detach(), b.detach(), a) for (w, b, a) in self._stack(self.priorMLP, L.ACT_LEAKY, L.ACT_LEAKY)]
+        hw, hb = self._heads(self.priorMu, self.priorLogvar)
+        layers.append((hw.detach(), hb.detach(), L.ACT_NONE))
+        first = ([cond] + user, layers, dict(latent=self.latent_size, **self._eps_args(B)))
+        nxt = [(w.detach(), b.detach(), a) for (w, b, a) in self._stack(next_mods, L.ACT_LEAKY, last_act)]
+
+        def second(res):
+            return [ops.Dense(res["z"]), cond] + user, nxt, {}
+
+        ra, rb = ops.mlp_forward_chain(first, second, B)
+        return ra["out"], ra["z"], rb["out"]
+
     def _encode_ids(self, s, r, u, reparam=False):
         """[docEmbed(s), onehot(r), user] -> enc_i (LeakyReLU each) -> [mu | logvar] (+ z).
         pivotcvae.py:250-260, 159-174."""

@@ -61,8 +61,7 @@ class UserListCVAEWithPrior(BaseCVAE):
         """listcvae.py:170-188."""
         with torch.no_grad():
             r, u, _ = self._inputs(r, u)
-            out, z = self._prior_block(r, u, reparam=True)
-            rx = self._decode(z, ("onehot", r), None if self.noUser else self._user_seg(u), [])
+            out, z, rx = self._prior_chain(r, u, self.decMLP)      # prior -> z -> decoder in one launch
             z_mu = out[:, :self.latent_size]
             if return_item:
                 return self.get_recommended_item(rx), z_mu

@@ -128,9 +128,10 @@ class UserPivotCVAE(BaseCVAE):
         """prior -> z -> pivot -> slate completion -> arg-max items (pivotcvae.py:278-296)."""
         with torch.no_grad():
             r, u, _ = self._inputs(r, u)
-            out, z = self._prior_block(r, u, reparam=True)
+            # prior -> z -> PSM in one launch, pivot pick, SCM, per-slot arg-max
+            out, z, pivot_output = self._prior_chain(r, u, self.psmMLP)
             user_seg = None if self.noUser else self._user_seg(u)
-            rx = self._decode(z, ("onehot", r), user_seg, [], None)
+            rx = self._scm(z, ("onehot", r), self._pick_index(pivot_output, None), user_seg, [])
             z_mu = out[:, :self.latent_size]
             if return_item:
                 return self.get_recommended_item(rx), z_mu

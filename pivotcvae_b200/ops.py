@@ -248,13 +248,9 @@ class Gather:
         keep.extend([self.table, self.idx])
 
 
-def mlp_forward(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
-                latent=0, eps=None, seed=0, offset=0, offset_dev=None):
-    """Run one fused MLP block.
-
-    segments: list of Dense/OneHot/Gather; layers: list of (W[n_out,n_in], b[n_out], act).
-    Returns dict(out=..., z=..., eps=..., x0=..., acts=[...]) (entries present when requested).
-    """
+def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
+              latent=0, eps=None, seed=0, offset=0, offset_dev=None):
+    """Build a pcv_mlp_desc (+ its output tensors); returns (desc, results, keep-alive list, device)."""
     if len(segments) > L.PCV_MAX_SEGMENTS or len(layers) > L.PCV_MAX_LAYERS:
         raise L.PcvError("too many segments / layers for one fused block")
     d = L.MlpDesc()
@@ -304,9 +300,30 @@ def mlp_forward(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_
             res["eps"] = eo
         d.seed, d.offset = int(seed), int(offset)
         d.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
+    return d, res, keep, dev
+
+
+def mlp_forward(segments, layers, B, **kw):
+    """Run one fused MLP block.
+
+    segments: list of Dense/OneHot/Gather; layers: list of (W[n_out,n_in], b[n_out], act).
+    Returns dict(out=..., z=..., eps=..., x0=..., acts=[...]) (entries present when requested).
+    """
+    d, res, keep, dev = _mlp_desc(segments, layers, B, **kw)
     with torch.cuda.device(dev), _timed("mlp_fwd"):
         L.check(L.load().pcv_mlp_fwd(ctypes.byref(d), int(B), _stream()), "pcv_mlp_fwd")
     return res
+
+
+def mlp_forward_chain(first, second_builder, B):
+    """Two chained blocks in one launch.  first = (segments, layers, kwargs); second_builder(res_first)
+    -> (segments, layers, kwargs) may reference the first block's output tensors (e.g. its z)."""
+    da, ra, ka, dev = _mlp_desc(first[0], first[1], B, **first[2])
+    segs_b, layers_b, kw_b = second_builder(ra)
+    db, rb, kb, _ = _mlp_desc(segs_b, layers_b, B, **kw_b)
+    with torch.cuda.device(dev), _timed("mlp_fwd2"):
+        L.check(L.load().pcv_mlp_fwd2(ctypes.byref(da), ctypes.byref(db), int(B), _stream()), "pcv_mlp_fwd2")
+    return ra, rb
 
 
 # ----------------------------------------------------------------------------
