@@ -504,12 +504,21 @@ def run_ours(args, w):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("bytes")
+    except Exception:
+        pass
     flops = 2.0 * D * N * (B * L_)
     ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "score_select_kernel<D=%d> (+finalize), M=%d rows x N=%d items" % (D, B * L_, N),
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 (B200_PROFILING.md)",
-                "traffic": None, "ms_avg_launch": dom["ms_avg"],
+                "traffic": traffic if not vp else None, "algorithmic_bytes": N * D * 4 + B * L_ * (D * 4 + 8),
+                "ms_avg_launch": dom["ms_avg"],
+                "epilogue_roofline": {"note": "at D=8 the consumer of the logits bounds the kernel (SURVEY H2): one ALU-pipe max slot "
+                                              "per logit = 64 logits/cycle/SM", "peak_logits_per_s": 64 * 148 * 1.965e9,
+                                      "frac": (B * L_) * N / (dom["ms_avg"] * 1e-3) / (64 * 148 * 1.965e9)},
                 "logits_per_s": (B * L_) * N / (dom["ms_avg"] * 1e-3),
                 "engine": args.engine, "share_of_step": dom["ms_avg"] / (ms / K) if dom["calls"] else None,
                 "timing": "CUDA events around the eager launch of the same call, %d steps after the timed region" % KP,
