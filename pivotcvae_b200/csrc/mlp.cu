@@ -27,7 +27,7 @@ namespace pcv {
 constexpr int MLP_THREADS = 256;
 constexpr int MLP_KC = 32;    // k-chunk staged per step
 constexpr int MLP_NB = 256;   // output columns per pass
-constexpr int MLP_WLD = MLP_NB + 4;
+constexpr int MLP_WLD_MAX = MLP_NB + 4;   // stage row stride: 257 (CT=1, conflict-free transposing stores) or 260
 
 struct MlpParams {
   pcv_mlp_desc d;
@@ -70,12 +70,13 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
   constexpr int CG = MLP_NB / CT;          // column groups (threads along n)
   constexpr int BM = RT * (THREADS / CG);  // batch rows per CTA
   constexpr int ALD = BM + 4;              // actT row stride (floats)
-  constexpr int KSPLIT = THREADS / MLP_NB; // threads sharing the staging of one weight column
-  constexpr int KPT = MLP_KC / KSPLIT;     // k values staged per thread and chunk
+  constexpr int MLP_WLD = (CT == 1) ? MLP_NB + 1 : MLP_NB + 4;
+  constexpr int NV4 = MLP_NB * MLP_KC / 4 / THREADS;   // float4 pieces of a weight chunk staged per thread
+  constexpr int NV1 = MLP_NB * MLP_KC / THREADS;       // scalar pieces (ragged chunks)
   const int ld = P.ld;              // max width (multiple of 4)
   float *actA = smem;               // [ld][ALD]
   float *actB = actA + ld * ALD;
-  float *wst = actB + ld * ALD;     // [2][MLP_KC][MLP_WLD]
+  float *wst = actB + ld * ALD;     // [2][MLP_KC][MLP_WLD]  (actB end is 16B-aligned: ld, ALD multiples of 4)
 
   const int tid = threadIdx.x;
   const int cg = tid % CG, rg = tid / CG;
@@ -84,23 +85,45 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 
   // ---------------- weight-chunk stream (layer, column block, k-chunk) ----------------
   int pl = 0, pnb = 0, pkc = 0;     // position of the chunk held in wv
-  float wv[KPT];
-  const int sn = tid % MLP_NB;              // weight column this thread stages
-  const int sk = (tid / MLP_NB) * KPT;      // first k (within the chunk) it stages
+  // Coalesced staging: 8 consecutive threads read one 128-byte row segment W[n][kc..kc+31]
+  // (a per-thread-row pattern costs 32 L1 wavefronts per warp load: it was the bottleneck).
+  float wv[NV1];
+  bool wvec = true;   // layout of wv: float4 pieces (full, 16B-aligned chunk) or scalars (ragged chunk)
   auto fetch = [&](int l, int nb, int kc) {
     const int K = d.layer[l].n_in, NO = d.layer[l].n_out;
-    const int n = nb + sn;
-    if (n < NO) {
-      const float *wrow = d.layer[l].W + (int64_t)n * K + kc + sk;
-      if (kc + MLP_KC <= K && ((K & 3) == 0)) {
+    wvec = (kc + MLP_KC <= K) && ((K & 3) == 0);
+    if (wvec) {
 #pragma unroll
-        for (int v = 0; v < KPT / 4; ++v) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4 *>(wrow) + v);
-          wv[4 * v] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
-        }
-      } else {
+      for (int i = 0; i < NV4; ++i) {
+        const int f = tid + THREADS * i;
+        const int n = nb + (f >> 3), c = f & 7;
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < NO) t4 = __ldg(reinterpret_cast<const float4 *>(d.layer[l].W + (int64_t)n * K + kc) + c);
+        wv[4 * i] = t4.x; wv[4 * i + 1] = t4.y; wv[4 * i + 2] = t4.z; wv[4 * i + 3] = t4.w;
+      }
+    } else {
 #pragma unroll
-        for (int kk = 0; kk < KPT; ++kk) wv[kk] = (kc + sk + kk < K) ? __ldg(wrow + kk) : 0.f;
+      for (int i = 0; i < NV1; ++i) {
+        const int e = tid + THREADS * i;
+        const int n = nb + (e >> 5), k = kc + (e & 31);
+        wv[i] = (n < NO && k < K) ? __ldg(d.layer[l].W + (int64_t)n * K + k) : 0.f;
+      }
+    }
+  };
+  auto stage = [&](float *ws) {   // registers -> transposed stage ws[kk][n]
+    if (wvec) {
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int f = tid + THREADS * i;
+        const int n = f >> 3, k = (f & 7) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ws[(k + j) * MLP_WLD + n] = wv[4 * i + j];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV1; ++i) {
+        const int e = tid + THREADS * i;
+        ws[(e & 31) * MLP_WLD + (e >> 5)] = wv[i];
       }
     }
   };
@@ -114,6 +137,15 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
     return pl < d.n_layers;
   };
   fetch(0, 0, 0);  // in flight during the prologue
+  // The whole weight set of the block (a few hundred KB) is requested into L2 up front, one
+  // 128-byte line per prefetch, so the chunk-by-chunk loads below hit L2 instead of paying the
+  // HBM latency once per chunk when the weights are cold (e.g. after an L2 flush).
+  for (int l = 0; l < d.n_layers; ++l) {
+    const char *wb = reinterpret_cast<const char *>(d.layer[l].W);
+    const int64_t bytes = (int64_t)d.layer[l].n_in * d.layer[l].n_out * 4;
+    for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)THREADS * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wb + o));
+  }
 
   // ---------------- prologue: assemble x0 into actA (transposed) ----------------
   {
@@ -190,10 +222,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 
       for (int kc = 0; kc < K; kc += MLP_KC) {
         float *ws = wst + buf * (MLP_KC * MLP_WLD);
-        if (nb + sn < L.n_out) {   // narrow layers: only the threads that own a real column stage it
-#pragma unroll
-          for (int kk = 0; kk < KPT; ++kk) ws[(sk + kk) * MLP_WLD + sn] = wv[kk];
-        }
+        stage(ws);
         __syncthreads();
         if (more) {
           more = advance();
@@ -201,14 +230,13 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
         }
         const int kmax = (nb + cg * CT < L.n_out) ? min(MLP_KC, K - kc) : 0;   // idle column groups skip the FMAs
         const float *ap = cur + (size_t)kc * ALD + rg * RT;
-        auto fma_step = [&](int kk) {
-          float a[RT];
+        // operands of step kk: RT activations (broadcast LDS.128) + CT weights
+        auto load_ops = [&](int kk, float (&a)[RT], float (&w)[CT]) {
 #pragma unroll
           for (int v = 0; v < RT / 4; ++v) {
             const float4 t4 = *reinterpret_cast<const float4 *>(ap + kk * ALD + 4 * v);
             a[4 * v] = t4.x; a[4 * v + 1] = t4.y; a[4 * v + 2] = t4.z; a[4 * v + 3] = t4.w;
           }
-          float w[CT];
           if (CT == 4) {
             const float4 t4 = *reinterpret_cast<const float4 *>(ws + kk * MLP_WLD + cg * 4);
             w[0] = t4.x; w[1 % CT] = t4.y; w[2 % CT] = t4.z; w[3 % CT] = t4.w;
@@ -218,17 +246,34 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
           } else {
             w[0] = ws[kk * MLP_WLD + cg];
           }
+        };
+        auto fma_ops = [&](const float (&a)[RT], const float (&w)[CT]) {
 #pragma unroll
           for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
         };
         if (kmax == MLP_KC) {
-          // full chunk: straight-line code so the shared-memory loads are hoisted ahead of the FMAs
+          // full chunk: explicit software pipeline, the operands of steps kk+1 and kk+2 are in flight
+          // while step kk's FMAs issue (shared-memory latency ~30 cycles, only 2-4 warps per scheduler)
+          float a0[RT], a1[RT], a2[RT], w0[CT], w1[CT], w2[CT];
+          load_ops(0, a0, w0);
+          load_ops(1, a1, w1);
 #pragma unroll
-          for (int kk = 0; kk < MLP_KC; ++kk) fma_step(kk);
+          for (int kk = 0; kk < MLP_KC; kk += 3) {
+            if (kk + 2 < MLP_KC) load_ops(kk + 2, a2, w2);
+            fma_ops(a0, w0);
+            if (kk + 3 < MLP_KC) load_ops(kk + 3, a0, w0);
+            if (kk + 1 < MLP_KC) fma_ops(a1, w1);
+            if (kk + 4 < MLP_KC) load_ops(kk + 4, a1, w1);
+            if (kk + 2 < MLP_KC) fma_ops(a2, w2);
+          }
         } else {
-          for (int kk = 0; kk < kmax; ++kk) fma_step(kk);
+          for (int kk = 0; kk < kmax; ++kk) {
+            float a[RT], w[CT];
+            load_ops(kk, a, w);
+            fma_ops(a, w);
+          }
         }
         buf ^= 1;
       }
@@ -407,7 +452,7 @@ static int mlp_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaS
   const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
   const int BM = 8 * CT;
   const int ld = Pb ? (Pa->ld > Pb->ld ? Pa->ld : Pb->ld) : Pa->ld;
-  size_t smem = (size_t)(2 * ld * (BM + 4) + 2 * MLP_KC * MLP_WLD) * sizeof(float);
+  size_t smem = (size_t)(2 * ld * (BM + 4) + 2 * MLP_KC * MLP_WLD_MAX) * sizeof(float);
   int64_t blocks = (B + BM - 1) / BM;
 #define PCV_MLP_LAUNCH(CTv, RTv, THv)                                                                              \
   if (Pb) {                                                                                                        \
