@@ -85,7 +85,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 
   // ---------------- weight-chunk stream (layer, column block, k-chunk) ----------------
   int pl = 0, pnb = 0, pkc = 0;     // position of the chunk held in wv
-  // Coalesced staging: 8 consecutive threads read one 128-byte row segment W[n][kc..kc+31]
+  // Coalesced staging: MLP_KC/4 consecutive threads read one contiguous row segment W[n][kc..kc+MLP_KC-1]
   // (a per-thread-row pattern costs 32 L1 wavefronts per warp load: it was the bottleneck).
   float wv[NV1];
   bool wvec = true;   // layout of wv: float4 pieces (full, 16B-aligned chunk) or scalars (ragged chunk)
@@ -96,7 +96,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
         const int f = tid + THREADS * i;
-        const int n = nb + (f >> 3), c = f & 7;
+        const int n = nb + f / (MLP_KC / 4), c = f % (MLP_KC / 4);
         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n < NO) t4 = __ldg(reinterpret_cast<const float4 *>(d.layer[l].W + (int64_t)n * K + kc) + c);
         wv[4 * i] = t4.x; wv[4 * i + 1] = t4.y; wv[4 * i + 2] = t4.z; wv[4 * i + 3] = t4.w;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 #pragma unroll
       for (int i = 0; i < NV1; ++i) {
         const int e = tid + THREADS * i;
-        const int n = nb + (e >> 5), k = kc + (e & 31);
+        const int n = nb + e / MLP_KC, k = kc + e % MLP_KC;
         wv[i] = (n < NO && k < K) ? __ldg(d.layer[l].W + (int64_t)n * K + k) : 0.f;
       }
     }
@@ -115,7 +115,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
         const int f = tid + THREADS * i;
-        const int n = f >> 3, k = (f & 7) * 4;
+        const int n = f / (MLP_KC / 4), k = (f % (MLP_KC / 4)) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) ws[(k + j) * MLP_WLD + n] = wv[4 * i + j];
       }
@@ -123,7 +123,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
 #pragma unroll
       for (int i = 0; i < NV1; ++i) {
         const int e = tid + THREADS * i;
-        ws[(e & 31) * MLP_WLD + (e >> 5)] = wv[i];
+        ws[(e % MLP_KC) * MLP_WLD + e / MLP_KC] = wv[i];
       }
     }
   };

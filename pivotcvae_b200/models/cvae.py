@@ -53,6 +53,7 @@ class BaseCVAE(nn.Module):
         st = self.__dict__.copy()
         st["_table"] = None
         st["_vp"] = None
+        st.pop("_head_cache", None)
         return st
 
     # ---- vocab-parallel scoring: every rank keeps the full fp32 table (<= 320 MB) for the
@@ -102,8 +103,20 @@ class BaseCVAE(nn.Module):
         return [(m.weight, m.bias, hidden_act if i < n - 1 else last_act) for i, m in enumerate(mods)]
 
     def _heads(self, mu_lin, lv_lin):
-        """The two latent heads as ONE linear layer emitting [mu | logvar]."""
-        return torch.cat([mu_lin.weight, lv_lin.weight], 0), torch.cat([mu_lin.bias, lv_lin.bias], 0)
+        """The two latent heads as ONE linear layer emitting [mu | logvar].  Under no_grad the
+        concatenation is cached until one of the four parameters changes (in-place updates bump
+        `_version`); with autograd on it is rebuilt so the gradient splits back onto the heads."""
+        if torch.is_grad_enabled():
+            return torch.cat([mu_lin.weight, lv_lin.weight], 0), torch.cat([mu_lin.bias, lv_lin.bias], 0)
+        key = (id(mu_lin), mu_lin.weight.data_ptr(), lv_lin.weight.data_ptr(), mu_lin.weight._version,
+               lv_lin.weight._version, mu_lin.bias._version, lv_lin.bias._version)
+        cache = self.__dict__.setdefault("_head_cache", {})
+        hit = cache.get(id(mu_lin))
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([mu_lin.weight, lv_lin.weight], 0).detach(),
+                   torch.cat([mu_lin.bias, lv_lin.bias], 0).detach())
+            cache[id(mu_lin)] = hit
+        return hit[1], hit[2]
 
     def _run_block(self, segs, layers, B, dense=(), **kw):
         """One fused MLP block; differentiable when grad mode is on."""
