@@ -87,6 +87,9 @@ typedef struct {
                                  captured CUDA graph draws fresh noise on every replay  */
 } pcv_select_opts;
 
+/* The workspace must be ZERO-FILLED once when it is allocated (the tcgen05 engine keeps a few
+ * counters in it and leaves them zeroed after every call); it may then be reused by any number of
+ * calls with the same table and M, one call at a time. */
 int pcv_score_select_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
 /* Q: [M, dim].  out_idx: [M] int64 (global index).  out_val: [M] fp32 (the
  * winning score; for exprace the winning key) or NULL. */

@@ -408,8 +408,9 @@ __global__ void __launch_bounds__(256)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
                  int64_t M, int n_split, int64_t items_per_split, float band_scale,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
-                 const unsigned long long *__restrict__ out_ent, const unsigned long long *__restrict__ row_best,
-                 int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
+                 const unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
+                 unsigned int *__restrict__ ovf_count_reset, int64_t *__restrict__ out_idx,
+                 float *__restrict__ out_val) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -478,6 +479,8 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   }
   if (lane == 0) {
     const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
+    row_best[row] = 0ull;                          // leave the workspace zeroed for the next call
+    if (row == 0) *ovf_count_reset = 0u;
     if (pb) {
       float ov;
       int32_t oi;
@@ -614,8 +617,8 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
   for (int64_t r0 = 0; r0 < M; r0 += Mg) {   // row groups reuse the workspace back to back on the stream
     const int64_t m = (M - r0 < Mg) ? (M - r0) : Mg;
     const float *Qg = Q + r0 * TC_D;
-    PCV_CUDA(cudaMemsetAsync(row_best, 0, (size_t)m * 8, st));
-    PCV_CUDA(cudaMemsetAsync(ovf_count, 0, 8, st));
+    // row_best / ovf_count are zero on entry: the workspace must be zero-initialised ONCE by the caller
+    // (see pcv_score_select_workspace_bytes) and tc_refine_kernel re-zeroes what a call dirtied
     dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)p.n_split);
     score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, p.items_per_split,
                                                            band_scale, rr, cc, ent, ovf_count, ovf_ent, ovf_row,
@@ -626,7 +629,7 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     PCV_LAUNCH_CHECK();
     tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, p.n_split,
                                                              p.items_per_split, band_scale, rr, cc, ent, row_best,
-                                                             out_idx + r0, out_val ? out_val + r0 : nullptr);
+                                                             ovf_count, out_idx + r0, out_val ? out_val + r0 : nullptr);
     PCV_LAUNCH_CHECK();
   }
   return PCV_OK;

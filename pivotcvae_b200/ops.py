@@ -125,7 +125,7 @@ class Table:
             n = ctypes.c_size_t()
             fn = L.load().pcv_score_select_workspace_bytes if kind == "select" else L.load().pcv_ce_workspace_bytes
             L.check(fn(self._h, int(M), ctypes.byref(n)), "workspace query")
-            ws = torch.empty(max(int(n.value), 256), dtype=torch.uint8, device=self.weight.device)
+            ws = torch.zeros(max(int(n.value), 256), dtype=torch.uint8, device=self.weight.device)  # zero-filled once (ABI contract)
             if len(self._ws) > 16:
                 self._ws.clear()
             self._ws[key] = ws
