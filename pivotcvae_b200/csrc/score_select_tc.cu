@@ -47,9 +47,10 @@ constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 4;
 
 struct __align__(1024) TcSmem {
   float b[TC_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
-  float a[TC_BM * TC_D];                       // query tile, same layout
+  float a[2][TC_BM * TC_D];                    // query tiles (double-buffered across work items), same layout
   unsigned long long cand[TC_SLICES][TC_CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
-  unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
+  float rmax[TC_BM];                           // running max per row, shared by the column slices
+  unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2], afull[2], aempty[2];
   uint32_t tmem_base;
 };
 
@@ -146,198 +147,253 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[1
   return max3(max3(a, b, c), g[9], g[10]);
 }
 
+// PERSISTENT: one CTA per SM loops over work items (row tile, catalog split); TMEM, the mbarrier
+// rings and the TMA pipeline live across items, so the per-item cost is just the tile stream
+// (matters for small catalogs, where an item is only ~18 tiles).  Roles:
+//   warp 0  : stages the NEXT item's 128 query rows into the double-buffered A tile (all lanes),
+//             then lane 0 streams that item's table tiles with TMA bulk copies;
+//   warp 1  : lane 0 issues one tcgen05.mma per tile (TMEM alloc/dealloc by the whole warp);
+//   warps 2+: epilogue (thread = query row x column slice).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
-                       const float *__restrict__ Q, int64_t M, int64_t items_per_split, float band_scale,
-                       float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
+                       const float *__restrict__ Q, int64_t M, int64_t items_per_split, int n_split, int n_work,
+                       float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
                        unsigned long long *__restrict__ out_ent, unsigned int *__restrict__ ovf_count,
                        unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cap) {
   extern __shared__ unsigned char smem_raw[];
   TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row_base = (int64_t)blockIdx.x * TC_BM;
-  const int64_t j_begin = (int64_t)blockIdx.y * items_per_split;
-  const int64_t j_end = min(n_rows, j_begin + items_per_split);
-  const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], TC_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], TC_EPI_WARPS);
+      mbar_init(&S.afull[b], 1); mbar_init(&S.aempty[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (warp >= 2 && warp < 6) {
-    // stage the 128 query rows: row t at byte t*32, 16-byte chunk c at ((c ^ bit2(t)) * 16)
-    const int t = threadIdx.x - 64;
-    const int64_t row = row_base + t;
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-    if (row < M) {
-      q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-      q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-    }
-    const int sw = (t >> 2) & 1;
-    float4 *dst = reinterpret_cast<float4 *>(S.a + t * TC_D);
-    dst[0 ^ sw] = q0;
-    dst[1 ^ sw] = q1;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
 
+  // work item w -> (row tile, split); consecutive items of a CTA walk the splits of nearby row tiles
+  // each CTA owns a CONTIGUOUS range of work items, so the splits of one row tile are mostly
+  // visited back to back by the same CTA and the rows' running maxima carry over between them
+  const int w_begin = (int)((int64_t)blockIdx.x * n_work / gridDim.x);
+  const int w_end = (int)((int64_t)(blockIdx.x + 1) * n_work / gridDim.x);
+  auto item_rows = [&](int w) { return (int64_t)(w / n_split) * TC_BM; };
+  // the splits of a row tile are visited in an order rotated by the tile index, so concurrent
+  // CTAs (which mostly hold different row tiles) stream different parts of the table
+  auto item_split = [&](int w) { return (w % n_split + (w / n_split) * 3) % n_split; };
+  auto item_jb = [&](int w) { return (int64_t)item_split(w) * items_per_split; };
+
   if (warp == 0) {
-    if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % TC_STAGES;
-        const uint32_t ph = (t / TC_STAGES) & 1;
-        mbar_wait(&S.empty[s], ph ^ 1);
-        const int64_t j0 = j_begin + (int64_t)t * TC_BN;
-        const uint32_t bytes = (uint32_t)min((int64_t)TC_TILE_BYTES, (n_rows - j0) * (int64_t)(TC_D * 4));
-        mbar_expect_tx(&S.full[s], bytes);  // rows past the end of the table keep stale data: masked below
-        tma_bulk_load(S.b[s], Wsw + j0 * TC_D, bytes, &S.full[s]);
+    // ---------------- producer: A tile of the item, then its table tiles ----------------
+    uint32_t gt = 0;   // tiles issued so far (ring position)
+    int it = 0;        // items started so far
+    for (int w = w_begin; w < w_end; ++w, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&S.aempty[ab], ((it >> 1) & 1) ^ 1);   // MMAs of the item that used this A buffer are done
+      {
+        // 128 query rows: row t at byte t*32, 16-byte chunk c at ((c ^ bit2(t)) * 16)  (SWIZZLE_32B image)
+        const int64_t row_base = item_rows(w);
+#pragma unroll
+        for (int i = 0; i < TC_BM / 32; ++i) {
+          const int t = lane + 32 * i;
+          const int64_t row = row_base + t;
+          float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+          if (row < M) {
+            q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+            q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+          }
+          const int sw = (t >> 2) & 1;
+          float4 *dst = reinterpret_cast<float4 *>(S.a[ab] + t * TC_D);
+          dst[0 ^ sw] = q0;
+          dst[1 ^ sw] = q1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.afull[ab]);
       }
+      if (lane == 0) {
+        const int64_t j_begin = item_jb(w);
+        const int64_t j_end = min(n_rows, j_begin + items_per_split);
+        const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
+        for (int t = 0; t < n_tiles; ++t, ++gt) {
+          const int s = gt % TC_STAGES;
+          const uint32_t ph = (gt / TC_STAGES) & 1;
+          mbar_wait(&S.empty[s], ph ^ 1);
+          const int64_t j0 = j_begin + (int64_t)t * TC_BN;
+          const uint32_t bytes = (uint32_t)min((int64_t)TC_TILE_BYTES, (n_rows - j0) * (int64_t)(TC_D * 4));
+          mbar_expect_tx(&S.full[s], bytes);  // rows past the end of the table keep stale data: masked below
+          tma_bulk_load(S.b[s], Wsw + j0 * TC_D, bytes, &S.full[s]);
+        }
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const uint64_t adesc = umma_desc_sw32(S.a);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % TC_STAGES;
-        const uint32_t ph = (t / TC_STAGES) & 1;
-        const int buf = t & 1;
-        const uint32_t bph = (t >> 1) & 1;
-        mbar_wait(&S.tempty[buf], bph ^ 1);
-        mbar_wait(&S.full[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        umma_tf32(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC, 0);
-        umma_commit(&S.empty[s]);
-        umma_commit(&S.tfull[buf]);
+      uint32_t gt = 0;
+      int it = 0;
+      for (int w = w_begin; w < w_end; ++w, ++it) {
+        const int ab = it & 1;
+        const int64_t j_begin = item_jb(w);
+        const int64_t j_end = min(n_rows, j_begin + items_per_split);
+        const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
+        mbar_wait(&S.afull[ab], (it >> 1) & 1);
+        const uint64_t adesc = umma_desc_sw32(S.a[ab]);
+        for (int t = 0; t < n_tiles; ++t, ++gt) {
+          const int s = gt % TC_STAGES;
+          const uint32_t ph = (gt / TC_STAGES) & 1;
+          const int buf = gt & 1;
+          const uint32_t bph = (gt >> 1) & 1;
+          mbar_wait(&S.tempty[buf], bph ^ 1);
+          mbar_wait(&S.full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          umma_tf32(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC, 0);
+          umma_commit(&S.empty[s]);
+          umma_commit(&S.tfull[buf]);
+        }
+        umma_commit(&S.aempty[ab]);   // fires when every MMA of this item has read the A tile
       }
     }
   } else {
-    // ---------------- epilogue: thread = (query row, column half) ----------------
+    // ---------------- epilogue: thread = (query row, column slice) ----------------
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
     const int slice = (warp - 2) >> 2;        // which TC_SW columns of every 256-column tile
     const int trow = quarter * 32 + lane;
-    const int64_t row = row_base + trow;
-    const bool live = row < M;
-    float q[TC_D];
-    {
-      float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-      if (live) {
-        q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-        q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-      }
-      q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
-    const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
-    // running max of the approximate scores; finite start so that masked (-inf) columns
-    // never pass, +inf for dummy rows so that nothing ever passes
-    float r = live ? -3.0e38f : INFINITY;
-    float thr = r;
-    int cnt = 0;
     unsigned long long *list = &S.cand[slice][0][trow];  // entry e at list[e * TC_BM]
-
-    bool ovf = false;
-    // rare: more chunks inside the band than a list holds -> append them to the global overflow
-    // buffer (exactly re-scored by tc_overflow_kernel); only if that is full too is the stream flagged
-    auto spill = [&](unsigned long long ent) {
-      const unsigned int pos = atomicAdd(ovf_count, 1u);
-      if (pos < ovf_cap) { ovf_ent[pos] = ent; ovf_row[pos] = (int32_t)row; }
-      else ovf = true;
-    };
-    // a full list is compacted in place: chunks whose approximate maximum fell out of the
-    // band of the (grown) running max can never hold the winner
-    auto compact = [&]() {
-      int k = 0;
-      for (int e = 0; e < cnt; ++e) {
-        const unsigned long long ent = list[e * TC_BM];
-        if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) list[(k++) * TC_BM] = ent;
-      }
-      cnt = k;
-    };
-
-    // one 32-column chunk: 16 FMNMX3 + one compare; a chunk whose approximate maximum is
-    // inside the band of the running max is only RECORDED (one shared-memory store) — the
-    // exact fp32 re-score happens in the refine kernel
-    auto process = [&](uint32_t (&v)[32], int32_t jb) {
-      float g[11];
-      const float m = chunk_max(v, g);
-      if (m >= thr) {
-        r = fmaxf(r, m);
-        thr = r - band;
-        if (cnt == TC_CAP) compact();
-        if (cnt < TC_CAP) {
-          list[cnt * TC_BM] = ((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb;
-          ++cnt;
-        } else {
-          spill(((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb);
+    uint32_t gt = 0;
+    int prev_tile = -1;
+    float r = 0.f, thr = 0.f, band = 0.f;   // per-row state, carried across the splits of a row tile
+    for (int w = w_begin; w < w_end; ++w) {
+      const int64_t row = item_rows(w) + trow;
+      const int64_t j_begin = item_jb(w);
+      const int64_t j_end = min(n_rows, j_begin + items_per_split);
+      const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
+      const bool live = row < M;
+      if (w / n_split != prev_tile) {   // new rows: reset the running max (any earlier maximum of the SAME row stays valid)
+        prev_tile = w / n_split;
+        float ss = 0.f;
+        if (live) {
+          const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+          const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+          ss = fmaf(q0.x, q0.x, ss); ss = fmaf(q0.y, q0.y, ss); ss = fmaf(q0.z, q0.z, ss); ss = fmaf(q0.w, q0.w, ss);
+          ss = fmaf(q1.x, q1.x, ss); ss = fmaf(q1.y, q1.y, ss); ss = fmaf(q1.z, q1.z, ss); ss = fmaf(q1.w, q1.w, ss);
         }
+        band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
+        // running max of the approximate scores; finite start so that masked (-inf) columns
+        // never pass, +inf for dummy rows so that nothing ever passes
+        r = live ? -3.0e38f : INFINITY;
+        thr = r;
+        S.rmax[trow] = -3.0e38f;   // shared with the other column slice of this row (benign race: monotone max)
       }
-    };
-    auto mask_tail = [&](uint32_t (&v)[32], int col0, int n_valid) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i >= n_valid) v[i] = 0xff800000u;  // -inf: zero-filled / foreign columns never win
-    };
-
-    constexpr int NCH = TC_SW / 32;  // chunks per slice per tile (even)
-    for (int t = 0; t < n_tiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t bph = (t >> 1) & 1;
-      mbar_wait(&S.tfull[buf], bph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * TC_SW;
-      const int n_valid = (int)min((int64_t)TC_SW, j_end - tile_j0);  // may be <= 0
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * TC_SW);
-      const int32_t jb0 = (int32_t)tile_j0;
-      uint32_t va[32], vb[32];
-      // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
-      TC_LD32(va, taddr);
-      TC_WAIT_LD(va);
-      if (n_valid == TC_SW) {
-#pragma unroll
-        for (int c = 0; c < NCH; c += 2) {
-          TC_LD32(vb, taddr + (c + 1) * 32);
-          process(va, jb0 + c * 32);
-          TC_WAIT_LD(vb);
-          if (c + 2 < NCH) TC_LD32(va, taddr + (c + 2) * 32);
-          process(vb, jb0 + (c + 1) * 32);
-          if (c + 2 < NCH) TC_WAIT_LD(va);
+      int cnt = 0;
+      bool ovf = false;
+      // rare: more chunks inside the band than a list holds -> append them to the global overflow
+      // buffer (exactly re-scored by tc_overflow_kernel); only if that is full too is the stream flagged
+      auto spill = [&](unsigned long long ent) {
+        const unsigned int pos = atomicAdd(ovf_count, 1u);
+        if (pos < ovf_cap) { ovf_ent[pos] = ent; ovf_row[pos] = (int32_t)row; }
+        else ovf = true;
+      };
+      // a full list is compacted in place: chunks whose approximate maximum fell out of the
+      // band of the (grown) running max can never hold the winner
+      auto compact = [&]() {
+        int k = 0;
+        for (int e = 0; e < cnt; ++e) {
+          const unsigned long long ent = list[e * TC_BM];
+          if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) list[(k++) * TC_BM] = ent;
         }
-      } else {  // last tile of the range: mask the columns beyond j_end
+        cnt = k;
+      };
+      // one 32-column chunk: 16 FMNMX3 + one compare; a chunk whose approximate maximum is
+      // inside the band of the running max is only RECORDED (one shared-memory store) — the
+      // exact fp32 re-score happens in the refine kernel
+      auto process = [&](uint32_t (&v)[32], int32_t jb) {
+        float g[11];
+        const float m = chunk_max(v, g);
+        if (m >= thr) {
+          r = fmaxf(r, m);
+          thr = r - band;
+          if (cnt == TC_CAP) compact();
+          if (cnt < TC_CAP) {
+            list[cnt * TC_BM] = ((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb;
+            ++cnt;
+          } else {
+            spill(((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb);
+          }
+        }
+      };
+      auto mask_tail = [&](uint32_t (&v)[32], int col0, int n_valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i >= n_valid) v[i] = 0xff800000u;  // -inf: stale / foreign columns never win
+      };
+
+      constexpr int NCH = TC_SW / 32;  // chunks per slice per tile (even)
+      for (int t = 0; t < n_tiles; ++t, ++gt) {
+        const int buf = gt & 1;
+        const uint32_t bph = (gt >> 1) & 1;
+        mbar_wait(&S.tfull[buf], bph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * TC_SW;
+        const int n_valid = (int)min((int64_t)TC_SW, j_end - tile_j0);  // may be <= 0
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * TC_SW);
+        const int32_t jb0 = (int32_t)tile_j0;
+        uint32_t va[32], vb[32];
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+        TC_LD32(va, taddr);
+        if (live && t < 4) {   // (first tiles of an item, while the TMEM load is in flight) exchange the running max with the other column slice
+          const float sh = S.rmax[trow];
+          if (sh > r) { r = sh; thr = r - band; }
+          else if (r > sh) S.rmax[trow] = r;
+        }
+        TC_WAIT_LD(va);
+        if (n_valid == TC_SW) {
+#pragma unroll
+          for (int c = 0; c < NCH; c += 2) {
+            TC_LD32(vb, taddr + (c + 1) * 32);
+            process(va, jb0 + c * 32);
+            TC_WAIT_LD(vb);
+            if (c + 2 < NCH) TC_LD32(va, taddr + (c + 2) * 32);
+            process(vb, jb0 + (c + 1) * 32);
+            if (c + 2 < NCH) TC_WAIT_LD(va);
+          }
+        } else {  // last tile of the range: mask the columns beyond j_end
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          if (c > 0) { TC_LD32(va, taddr + c * 32); TC_WAIT_LD(va); }
-          mask_tail(va, c * 32, n_valid);
-          process(va, jb0 + c * 32);
+          for (int c = 0; c < NCH; ++c) {
+            if (c > 0) { TC_LD32(va, taddr + c * 32); TC_WAIT_LD(va); }
+            mask_tail(va, c * 32, n_valid);
+            process(va, jb0 + c * 32);
+          }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.tempty[buf]);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.tempty[buf]);
-    }
-    if (live) {
-      // hand the surviving chunks of this (split, slice) stream to the refine kernel
-      const int64_t stream = (int64_t)blockIdx.y * TC_SLICES + slice;
-      int k = 0;
-      for (int e = 0; e < cnt; ++e) {
-        const unsigned long long ent = list[e * TC_BM];
-        if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) {
-          if (k < TC_OUT) out_ent[(stream * TC_OUT + k) * M + row] = ent;
-          else spill(ent);
-          ++k;
+      if (live) {
+        // hand the surviving chunks of this (split, slice) stream to the refine kernel
+        const int64_t stream = (int64_t)item_split(w) * TC_SLICES + slice;
+        int k = 0;
+        for (int e = 0; e < cnt; ++e) {
+          const unsigned long long ent = list[e * TC_BM];
+          if (__uint_as_float((uint32_t)(ent >> 32)) >= thr) {
+            if (k < TC_OUT) out_ent[(stream * TC_OUT + k) * M + row] = ent;
+            else spill(ent);
+            ++k;
+          }
         }
+        out_r[stream * M + row] = r;
+        out_cnt[stream * M + row] = ovf ? -1 : min(k, TC_OUT);
       }
-      out_r[stream * M + row] = r;
-      out_cnt[stream * M + row] = ovf ? -1 : min(k, TC_OUT);
     }
   }
 
@@ -619,10 +675,11 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     const float *Qg = Q + r0 * TC_D;
     // row_best / ovf_count are zero on entry: the workspace must be zero-initialised ONCE by the caller
     // (see pcv_score_select_workspace_bytes) and tc_refine_kernel re-zeroes what a call dirtied
-    dim3 grid((unsigned)((m + TC_BM - 1) / TC_BM), (unsigned)p.n_split);
+    const int64_t n_work = ((m + TC_BM - 1) / TC_BM) * (int64_t)p.n_split;
+    const unsigned grid = (unsigned)(n_work < t->sm_count ? n_work : t->sm_count);   // persistent: <= one CTA per SM
     score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, p.items_per_split,
-                                                           band_scale, rr, cc, ent, ovf_count, ovf_ent, ovf_row,
-                                                           p.ovf_cap);
+                                                           p.n_split, (int)n_work, band_scale, rr, cc, ent, ovf_count,
+                                                           ovf_ent, ovf_row, p.ovf_cap);
     PCV_LAUNCH_CHECK();
     tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Qg, ovf_count, ovf_ent, ovf_row, p.ovf_cap,
                                                     row_best);
