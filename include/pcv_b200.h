@@ -214,6 +214,15 @@ int pcv_ce_fwd_bwd(const pcv_table *t, const float *Q, const int64_t *targets,
                    float *dq, void *workspace, size_t workspace_bytes,
                    pcv_stream_t stream);
 
+/* Candidate-mode (sampled soft-max) CE — the reference's default training mode
+ * (train_generative.py:52-56; pivotcvae.py:265-271, listcvae.py:157-163):
+ * p[i, c] = <W[candidates[i, c]], q_i>, loss_rows[i] = CE(p[i, :], target_pos[i]).
+ * candidates: [M, n_cand] int64 item ids, target_pos: [M] int64 column of the target.
+ * dq[i, :] = d loss_rows[i] / d q_i; logits_out (optional) = p [M, n_cand]. */
+int pcv_cand_ce_fwd_bwd(const pcv_table *t, const float *Q, const int64_t *candidates,
+                        const int64_t *target_pos, int64_t M, int n_cand, float *loss_rows,
+                        float *lse, float *dq, float *logits_out, pcv_stream_t stream);
+
 /* ------------------------------------------------------------------ */
 /* Simulator response models, gather-plus-dot (env/response_model.py)  */
 /*   URM      :129-150   URM_P :286-295   URM_P_MR :315-323            */

@@ -179,6 +179,20 @@ def ce(W, Q, targets, bitmask=None):
     return loss, lse, dq
 
 
+def cand_ce(W, Q, candidates, target_pos):
+    """-> (loss_rows[M], dq[M, D], p[M, nC]) for the sampled soft-max mode."""
+    W, Q = _f32(W), _f32(Q)
+    M, D = Q.shape
+    cand = _i64(candidates).reshape(M, -1)
+    tpos = _i64(target_pos).reshape(-1)
+    nC = cand.shape[1]
+    loss = np.empty(M, dtype=np.float32)
+    dq = np.empty((M, D), dtype=np.float32)
+    p = np.empty((M, nC), dtype=np.float32)
+    lib().orc_cand_ce(_p(W), I32(D), _p(Q), _p(cand), _p(tpos), I64(M), I32(nC), _p(loss), _p(dq), _p(p))
+    return loss, dq, p
+
+
 def kl(mu, lv, pmu, plv, grads=False):
     mu, lv, pmu, plv = _f32(mu), _f32(lv), _f32(pmu), _f32(plv)
     if grads:
@@ -339,6 +353,18 @@ def gen_loss(sd, s, r, u, eps, no_user, beta, bitmask=None, model="pivot", train
     W = _f32(sd["docEmbed.weight"])
     q = f["rx"].reshape(-1, W.shape[1])
     loss_rows, _, _ = ce(W, q, _i64(s).reshape(-1), bitmask)
+    rec = float(np.mean(loss_rows.astype(np.float64)))
+    kld = kl(f["z_mu"], f["z_logvar"], pmu, plv)
+    return rec + beta * kld, rec, kld
+
+
+def gen_loss_candidates(sd, s, r, u, eps, no_user, beta, candidates, target_pos, model="pivot"):
+    """get_gen_loss, candidate branch (train_generative.py:52-56) -> (loss, recLoss, KLD)."""
+    pmu, plv = prior(sd, r, u, no_user)
+    f = pivot_forward(sd, s, r, u, eps, no_user, "gt") if model == "pivot" else list_forward(sd, s, r, u, eps, no_user)
+    W = _f32(sd["docEmbed.weight"])
+    q = f["rx"].reshape(-1, W.shape[1])
+    loss_rows, _, _ = cand_ce(W, q, candidates, target_pos)
     rec = float(np.mean(loss_rows.astype(np.float64)))
     kld = kl(f["z_mu"], f["z_logvar"], pmu, plv)
     return rec + beta * kld, rec, kld

@@ -371,6 +371,40 @@ void orc_ce(const float *W, int64_t N, int D, const float *Q, const int64_t *tar
   parallel_for(M, 4, ce_body, &c);
 }
 
+/* ---- candidate-mode CE: train_generative.py:52-56 with p = bmm(docEmbed(candidates), prox)
+ * (pivotcvae.py:265-271).  cand: [M, nC] item ids, tpos: [M] target column. ---- */
+void orc_cand_ce(const float *W, int D, const float *Q, const int64_t *cand, const int64_t *tpos, int64_t M, int nC,
+                 float *loss_rows, float *dq, float *logits) {
+  for (int64_t i = 0; i < M; ++i) {
+    const float *q = Q + i * D;
+    float mx = -INFINITY;
+    for (int c = 0; c < nC; ++c) {
+      const float *w = W + cand[i * nC + c] * D;
+      float s = 0.f;
+      for (int k = 0; k < D; ++k) s = fmaf(w[k], q[k], s);
+      if (logits) logits[i * nC + c] = s;
+      if (s > mx) mx = s;
+    }
+    double L = 0.0, acc[128];
+    for (int k = 0; k < D; ++k) acc[k] = 0.0;
+    float st = 0.f;
+    for (int c = 0; c < nC; ++c) {
+      const float *w = W + cand[i * nC + c] * D;
+      float s = 0.f;
+      for (int k = 0; k < D; ++k) s = fmaf(w[k], q[k], s);
+      if (c == tpos[i]) st = s;
+      double pr = exp((double)s - (double)mx);
+      L += pr;
+      for (int k = 0; k < D; ++k) acc[k] += pr * (double)w[k];
+    }
+    if (loss_rows) loss_rows[i] = (float)((double)mx + log(L) - (double)st);
+    if (dq) {
+      const float *wt = W + cand[i * nC + tpos[i]] * D;
+      for (int k = 0; k < D; ++k) dq[i * D + k] = (float)(acc[k] / L - (double)wt[k]);
+    }
+  }
+}
+
 /* ---- train_generative.py:61  KLD = -0.5 * sum(1 + lv - plv - (exp(lv) + (mu-pmu)^2)/exp(plv)) ---- */
 double orc_kl(const float *mu, const float *lv, const float *pmu, const float *plv, int64_t n,
               float *dmu, float *dlv, float *dpmu, float *dplv) {

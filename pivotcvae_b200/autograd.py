@@ -163,3 +163,37 @@ class LogitsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dp):
         return dp.mm(ctx.table.weight), None
+
+
+class CandidateCEFn(torch.autograd.Function):
+    """mean CE over per-row candidate lists (train_generative.py:52-56)."""
+
+    @staticmethod
+    def forward(ctx, q, table, candidates, target_pos):
+        loss_rows, lse, dq, _ = ops.cand_ce_fwd_bwd(table, q, candidates, target_pos, want_dq=q.requires_grad)
+        ctx.M = q.shape[0]
+        if dq is not None:
+            ctx.save_for_backward(dq)
+        return loss_rows.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        (dq,) = ctx.saved_tensors
+        return dq * (g / ctx.M), None, None, None
+
+
+class CandidateLogitsFn(torch.autograd.Function):
+    """p[i, c] = <W[cand[i, c]], q_i> materialised (forward()'s candidate branch, pivotcvae.py:265-271)."""
+
+    @staticmethod
+    def forward(ctx, q, table, candidates):
+        M = q.shape[0]
+        tp = torch.zeros(M, dtype=torch.int64, device=q.device)
+        _, _, _, p = ops.cand_ce_fwd_bwd(table, q, candidates, tp, want_dq=False, want_logits=True)
+        ctx.table, ctx.cand = table, candidates
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        w = ctx.table.weight[ctx.cand.reshape(dp.shape[0], -1)]          # (M, nC, D) plain gather
+        return torch.bmm(dp.unsqueeze(1), w).squeeze(1), None, None

@@ -403,6 +403,80 @@ static int launch_ce_sparse(const Table *t, const float *Q, const int64_t *targe
   return PCV_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Candidate-mode (sampled soft-max) cross-entropy — the reference's default training
+// mode (train_generative.py:52-56; pivotcvae.py:265-271 / listcvae.py:157-163):
+//   p[i, c] = <docEmbed[cand[i, c]], q_i>   (gather + bmm),   loss_i = CE(p[i, :], tgt_pos[i])
+// One warp per row: lanes stride over the nC candidates, gather the 32-byte rows,
+// exact FMA-chain logit, online soft-max, dq accumulate; duplicates in the candidate
+// list count once per occurrence, exactly like the reference's bmm + CrossEntropyLoss.
+// Optionally materialises p (forward()'s first return value).
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+cand_ce_kernel(const float *__restrict__ W, const float *__restrict__ Q, const int64_t *__restrict__ cand,
+               const int64_t *__restrict__ tgt_pos, int64_t M, int nC, float *__restrict__ loss_rows,
+               float *__restrict__ lse_out, float *__restrict__ dq, float *__restrict__ logits_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float q[D];
+#pragma unroll
+  for (int c = 0; c < D / 4; ++c) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(Q + row * D) + c);
+    q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+  }
+  float m = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) acc[k] = 0.f;
+  const int64_t *cr = cand + row * nC;
+  for (int c = lane; c < nC; c += 32) {
+    const int64_t j = __ldg(cr + c);
+    float w[D];
+#pragma unroll
+    for (int v4 = 0; v4 < D / 4; ++v4) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(W + j * D) + v4);
+      w[4 * v4] = v.x; w[4 * v4 + 1] = v.y; w[4 * v4 + 2] = v.z; w[4 * v4 + 3] = v.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s = fmaf(w[k], q[k], s);   // bmm(candidateEmb, prox): row of W first
+    if (logits_out) logits_out[row * nC + c] = s;
+    if (s > m) {
+      const float sc = __expf(m - s);
+      l *= sc;
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc[k] *= sc;
+      m = s;
+    }
+    const float p = __expf(s - m);
+    l += p;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = fmaf(p, w[k], acc[k]);
+  }
+  const float mw = warp_max(m);
+  const float sc = (m == -INFINITY) ? 0.f : __expf(m - mw);
+  const float L = warp_sum(l * sc);
+  float a[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) a[k] = warp_sum(acc[k] * sc);
+  if (lane == 0) {
+    const float lse = mw + logf(L);
+    const int64_t jt = cr[tgt_pos[row]];
+    const float *wt = W + jt * D;
+    float xt = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) xt = fmaf(wt[k], q[k], xt);
+    if (loss_rows) loss_rows[row] = lse - xt;
+    if (lse_out) lse_out[row] = lse;
+    if (dq) {
+      const float inv = 1.f / L;
+#pragma unroll
+      for (int k = 0; k < D; ++k) dq[row * D + k] = a[k] * inv - wt[k];
+    }
+  }
+}
+
 template <int D, int MODE>
 static int launch_ce(const Table *t, const CEPlan &p, const float *Q, const int64_t *targets,
                      int64_t M, const uint32_t *bitmask, int64_t mask_words, uint64_t seed,
@@ -443,6 +517,31 @@ static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const in
 using namespace pcv;
 
 extern "C" {
+
+int pcv_cand_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *candidates, const int64_t *target_pos,
+                        int64_t M, int n_cand, float *loss_rows, float *lse, float *dq, float *logits_out,
+                        pcv_stream_t stream) {
+  PCV_CHECK_ARG(th && Q && candidates && target_pos, "NULL pointer");
+  PCV_CHECK_ARG(M > 0 && n_cand > 0, "bad shape");
+  const Table *t = reinterpret_cast<const Table *>(th);
+  PCV_CHECK_ARG(t->row_offset == 0, "candidate CE needs the whole table (row_offset 0)");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((M + 7) / 8);
+  switch (t->dim) {
+    case 4: cand_ce_kernel<4><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    case 8: cand_ce_kernel<8><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    case 16: cand_ce_kernel<16><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    case 32: cand_ce_kernel<32><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    case 64: cand_ce_kernel<64><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    default:
+      set_error("cand_ce: dim %d unsupported", t->dim);
+      return PCV_ERR_UNSUPPORTED;
+  }
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
 
 int pcv_ce_workspace_bytes(const pcv_table *th, int64_t M, size_t *bytes_host) {
   PCV_CHECK_ARG(th && bytes_host, "NULL pointer");

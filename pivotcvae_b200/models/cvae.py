@@ -268,6 +268,11 @@ class BaseCVAE(nn.Module):
         Z = self.latent_size
         return out[:, :Z], out[:, Z:]
 
-    def _logits(self, rx_flat):
-        from ..autograd import LogitsFn
+    def _logits(self, rx_flat, candidates=None):
+        """forward()'s `p`: scores against the whole table, or (candidateFlag) against the per-slot
+        candidate lists (B, L, nC) as pivotcvae.py:265-271 does with gather + bmm."""
+        from ..autograd import CandidateLogitsFn, LogitsFn
+        if self.candidateFlag:
+            cand = candidates.to(self._dev(), torch.int64).reshape(rx_flat.shape[0], -1)
+            return CandidateLogitsFn.apply(rx_flat, self.item_table(), cand)
         return LogitsFn.apply(rx_flat, self.item_table())

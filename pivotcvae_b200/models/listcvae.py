@@ -50,11 +50,9 @@ class UserListCVAEWithPrior(BaseCVAE):
 
     def forward(self, s, r, candidates=None, u=None):
         """-> (p, rx, z, emb, z_mu, z_logvar) as listcvae.py:134-168 (rx stays (B, L*D) there)."""
-        if self.candidateFlag:
-            raise NotImplementedError("candidate-mode (sampled soft-max) training is SURVEY §8(f) N1: not built yet")
         rx, z, mu, lv, s = self.forward_latent(s, r, u)
         emb = self.docEmbed.weight[s.reshape(-1)].view(s.shape[0], -1)  # returned for API parity only
-        p = self._logits(rx.view(-1, self.feature_size))
+        p = self._logits(rx.view(-1, self.feature_size), candidates)
         return p, rx, z, emb, mu, lv
 
     def recommend(self, r, u=None, return_item=False):

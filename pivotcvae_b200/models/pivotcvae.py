@@ -115,13 +115,10 @@ class UserPivotCVAE(BaseCVAE):
 
     def forward(self, s, r, candidates=None, u=None):
         """-> (p, rx, z, emb, z_mu, z_logvar) as pivotcvae.py:242-276."""
-        if self.candidateFlag:
-            raise NotImplementedError("candidate-mode (sampled soft-max) training is SURVEY §8(f) N1: not built yet; "
-                                      "use mask training (candidateFlag=False)")
         rx, z, mu, lv, s = self.forward_latent(s, r, u)
         B = s.shape[0]
         emb = self.docEmbed.weight[s.reshape(-1)].view(B, -1)  # returned for API parity only
-        p = self._logits(rx.view(-1, self.feature_size))
+        p = self._logits(rx.view(-1, self.feature_size), candidates)
         return p, rx.view(B, self.slate_size, self.feature_size), z, emb, mu, lv
 
     def recommend(self, r, u=None, return_item=False, random_pivot=False):

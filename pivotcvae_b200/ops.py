@@ -364,6 +364,23 @@ def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0,
     return loss, lse, dq
 
 
+def cand_ce_fwd_bwd(table, Q, candidates, target_pos, want_dq=True, want_logits=False):
+    """Sampled soft-max CE over per-row candidate lists -> (loss_rows[M], lse[M], dq[M,D]|None, p[M,nC]|None)."""
+    Q = _f32(Q, "Q")
+    M, D = Q.shape
+    candidates = _i64(candidates, "candidates").reshape(M, -1)
+    target_pos = _i64(target_pos, "target_pos").reshape(-1)
+    nC = candidates.shape[1]
+    loss = torch.empty(M, dtype=torch.float32, device=Q.device)
+    lse = torch.empty(M, dtype=torch.float32, device=Q.device)
+    dq = torch.empty(M, D, dtype=torch.float32, device=Q.device) if want_dq else None
+    p = torch.empty(M, nC, dtype=torch.float32, device=Q.device) if want_logits else None
+    with torch.cuda.device(Q.device), _timed("cand_ce_fwd_bwd"):
+        L.check(L.load().pcv_cand_ce_fwd_bwd(table.handle, _ptr(Q), _ptr(candidates), _ptr(target_pos), M, nC, _ptr(loss),
+                                             _ptr(lse), _ptr(dq), _ptr(p), _stream()), "pcv_cand_ce_fwd_bwd")
+    return loss, lse, dq, p
+
+
 def urm_forward(variant, doc, usr, item_bias, user_bias, slates, users, pos_bias=None, pos_dep=None, mr_factor=0.0):
     doc, usr = _f32(doc), _f32(usr)
     ib, ub = _f32(item_bias).reshape(-1), _f32(user_bias).reshape(-1)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .autograd import CatalogCEFn, KLFn
+from .autograd import CatalogCEFn, KLFn  # noqa: F401
 from .env.response_model import sample_users
 from .models.listcvae import UserListCVAEWithPrior
 from .models.pivotcvae import PIVOTCVAE_MODELS
@@ -40,9 +40,16 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
     users = _as_tensor(batch_data["users"], torch.int64, dev)
     targets = _as_tensor(batch_data["responses"], torch.float32, dev)
     pMu, pLogvar = model.get_prior(targets, users)
-    if model.candidateFlag:
-        raise NotImplementedError("candidate-mode training is SURVEY §8(f) N1: not built yet (use --mask_train)")
     rx, z, mu, logvar, _ = model.forward_latent(slates, targets, users)
+    if model.candidateFlag:
+        # sampled soft-max over the data loader's candidates (train_generative.py:52-56): fused gather-dot-CE
+        from .autograd import CandidateCEFn
+        M = slates.numel()
+        cand = _as_tensor(batch_data["sample_candidates"], torch.int64, dev).reshape(M, -1)
+        tpos = _as_tensor(batch_data["sample_targets"], torch.int64, dev).reshape(-1)
+        recLoss = CandidateCEFn.apply(rx.reshape(M, -1), model.item_table(), cand, tpos)
+        KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
+        return recLoss + beta * KLD, recLoss, KLD
     if getattr(model, "_vp", None) is not None:
         raise NotImplementedError("vocab-parallel training (CE partials + dQ all-reduce) is not built yet; "
                                   "train data-parallel with the replicated table")

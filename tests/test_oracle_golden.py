@@ -184,3 +184,19 @@ def test_threads_do_not_change_results(golden):
     finally:
         oracle.set_threads(1)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("kind", ["pivot", "list"])
+def test_candidate_mode_loss(golden, kind):
+    """Sampled soft-max training (the reference's default, train_generative.py:52-56): candidates drawn
+    by the reference's own Dataset sampler (data_loader.py:49-58)."""
+    fx = golden("cand_small")
+    sd = fx.sub(kind + "/sd/")
+    got = oracle.gen_loss_candidates(sd, fx["in/slates"], fx["in/resp"], fx["in/users"], fx[kind + "/eps"], False, 0.01,
+                                     fx["in/candidates"], fx["in/targets"], kind)
+    np.testing.assert_allclose(got, fx[kind + "/loss"], rtol=1e-4)
+    f = (oracle.pivot_forward(sd, fx["in/slates"], fx["in/resp"], fx["in/users"], fx[kind + "/eps"], False, "gt")
+         if kind == "pivot" else oracle.list_forward(sd, fx["in/slates"], fx["in/resp"], fx["in/users"], fx[kind + "/eps"], False))
+    W = sd["docEmbed.weight"]
+    _, _, p = oracle.cand_ce(W, f["rx"].reshape(-1, 8), fx["in/candidates"], fx["in/targets"])
+    np.testing.assert_allclose(p, fx[kind + "/p"], rtol=1e-4, atol=1e-5)
