@@ -137,7 +137,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -200,7 +200,7 @@ def time_cpu(w, sd, env_sd, mode, B, steps, warmup, min_seconds=0.0):
             times.append(dt)
             t_total += dt
         i += 1
-        if len(times) >= 200:
+        if len(times) >= 2000:
             break
     return float(np.mean(times)), threads, len(times)
 
@@ -511,7 +511,10 @@ def run_ours(args, w):
         pass
     flops = 2.0 * D * N * (B * L_)
     ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "score_select_kernel<D=%d> (+finalize), M=%d rows x N=%d items" % (D, B * L_, N),
+    tc = args.engine in ("auto", "tcgen05") and D == 8 and N >= 2048 and mode != "sampled_all"
+    kname = ("score_select_tc_kernel (tcgen05 tf32 filter) + tc_overflow + tc_refine (exact fp32)" if tc
+             else "score_select_kernel<D=%d> (exact fp32 SIMT) + finalize" % D)
+    roofline = {"bound": "tensor", "kernel": "%s, M=%d rows x N=%d items" % (kname, B * L_, N),
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 (B200_PROFILING.md)",
                 "traffic": traffic if not vp else None, "algorithmic_bytes": N * D * 4 + B * L_ * (D * 4 + 8),
