@@ -252,6 +252,7 @@ def run_train(args, w):
     sd, env_sd = make_weights(w, "pivot")
     model, _ = build_gpu(w, sd, env_sd, "greedy", device)
     model.noise.reseed(99 + rank)
+    model.ce_engine = args.ce_engine
     n_neg = w["n_items"] if args.n_neg <= 0 else args.n_neg
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=(world == 1))
     params = [p for p in model.parameters() if p.requires_grad]
@@ -352,8 +353,9 @@ def run_train(args, w):
     ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
     line = {"metric": "train samples/sec (PivotCVAE gt, fused catalog CE + KL, fwd+bwd+Adam)", "value": total / (ms / 1e3),
             "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "batch_per_gpu": B, "n_neg": n_neg, "beta": 0.001,
+            "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 logits, f32 accumulate" if (args.ce_engine == "tf32" and keep >= 1.0) else "f32"),
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "batch_per_gpu": B, "n_neg": n_neg, "beta": 0.001, "ce_engine": args.ce_engine,
                        "parallelism": "dp%d (replicated table, grad all-reduce)" % world,
                        "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed"},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": "samples/s",
@@ -557,6 +559,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="greedy", choices=["greedy", "sampled", "list", "train"])
     ap.add_argument("--n-neg", type=int, default=0, help="train mode: negatives per row (0 = the whole catalog)")
+    ap.add_argument("--ce-engine", default="tf32", choices=["exact", "tf32"],
+                    help="train mode, full catalog: CE logits in exact fp32 (SIMT) or tf32 on the tensor cores (C3 is a reduced-precision config)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--parallel", default="dp", choices=["dp", "vp"], help="N>1: batch data-parallel (default) or vocab-parallel")

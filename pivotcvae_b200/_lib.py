@@ -54,7 +54,7 @@ class MlpDesc(ctypes.Structure):
 
 class CeMask(ctypes.Structure):
     _fields_ = [("keep_prob", ctypes.c_double), ("bitmask", c_void_p), ("seed", c_uint64),
-                ("offset", c_uint64), ("offset_dev", c_void_p)]
+                ("offset", c_uint64), ("offset_dev", c_void_p), ("engine", c_int)]
 
 
 class UrmDesc(ctypes.Structure):

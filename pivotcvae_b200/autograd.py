@@ -119,9 +119,9 @@ class CatalogCEFn(torch.autograd.Function):
     (train_generative.py:36-42, 59) without materialising logits."""
 
     @staticmethod
-    def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset, offset_dev=None):
+    def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset, offset_dev=None, engine="exact"):
         loss_rows, lse, dq = ops.ce_fwd_bwd(table, q, targets, keep_prob, bitmask, seed, offset,
-                                            want_dq=q.requires_grad, offset_dev=offset_dev)
+                                            want_dq=q.requires_grad, offset_dev=offset_dev, engine=engine)
         ctx.M = q.shape[0]
         if dq is not None:
             ctx.save_for_backward(dq)
@@ -135,7 +135,7 @@ class CatalogCEFn(torch.autograd.Function):
         d = dq * scale
         if g_rows is not None:
             d = d + dq * g_rows.unsqueeze(1)
-        return d, None, None, None, None, None, None, None
+        return d, None, None, None, None, None, None, None, None
 
 
 class KLFn(torch.autograd.Function):

@@ -512,6 +512,11 @@ static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const in
   return PCV_ERR_UNSUPPORTED;
 }
 
+// tensor-core engine (ce_tc.cu)
+bool ce_tc_supported(const Table *t);
+size_t ce_tc_workspace(const Table *t, int64_t M);
+int ce_tc_launch(const Table *t, const float *Q, int64_t M, float *part, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace pcv
 
 using namespace pcv;
@@ -552,7 +557,10 @@ int pcv_ce_workspace_bytes(const pcv_table *th, int64_t M, size_t *bytes_host) {
     set_error("ce: dim %d unsupported", t->dim);
     return PCV_ERR_UNSUPPORTED;
   }
-  *bytes_host = (p.ws_bytes + 255) & ~(size_t)255;
+  size_t b = p.ws_bytes;
+  const size_t tc = ce_tc_workspace(t, M);
+  if (tc > b) b = tc;
+  *bytes_host = (b + 255) & ~(size_t)255;
   return PCV_OK;
 }
 
@@ -572,7 +580,7 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
     set_error("ce: dim %d unsupported", t->dim);
     return PCV_ERR_UNSUPPORTED;
   }
-  if (!workspace || workspace_bytes < p.ws_bytes) {
+  if (!workspace || (workspace_bytes < p.ws_bytes && mask->engine != PCV_CE_ENGINE_TF32)) {
     set_error("ce: workspace too small (%zu < %zu)", workspace_bytes, p.ws_bytes);
     return PCV_ERR_WORKSPACE;
   }
@@ -581,6 +589,17 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
   const int64_t mask_words = (t->n_rows + 31) / 32;
   if (mask->bitmask) {
     rc = ce_dispatch<CE_BITMASK>(t, p, Q, targets, M, mask->bitmask, mask_words, 0, 0, nullptr, 0, part, st);
+  } else if (mask->keep_prob >= 1.0 && mask->engine == PCV_CE_ENGINE_TF32) {
+    if (!ce_tc_supported(t)) {
+      set_error("ce: the tf32 engine needs dim 8 and an unsharded table");
+      return PCV_ERR_UNSUPPORTED;
+    }
+    const int n_parts = ce_tc_launch(t, Q, M, part, workspace_bytes, st);
+    if (n_parts < 0) return n_parts;
+    ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(part, n_parts, M, t->dim, t->W, t->n_rows,
+                                                                    t->row_offset, Q, targets, loss_rows, lse, dq);
+    PCV_LAUNCH_CHECK();
+    return PCV_OK;
   } else if (mask->keep_prob >= 1.0) {
     rc = ce_dispatch<CE_DENSE>(t, p, Q, targets, M, nullptr, 0, 0, 0, nullptr, 0, part, st);
   } else {

@@ -45,6 +45,7 @@ class BaseCVAE(nn.Module):
                              "(every reference subclass hard-codes fine_tune=False)")
         self.noise = NoiseSource()
         self.select_engine = "auto"
+        self.ce_engine = "exact"   # "tf32": full-catalog CE logits on the tensor cores (reduced-precision tolerance)
         self._table = None
         self._vp = None      # vocab-parallel state: (group, lo, hi) once enable_vocab_parallel() is called
 

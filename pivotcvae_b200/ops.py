@@ -339,7 +339,8 @@ def kl_fwd_bwd(mu, logvar, pmu, plogvar, grads=True):
     return out, g
 
 
-def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0, want_dq=True, offset_dev=None):
+def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0, want_dq=True, offset_dev=None,
+               engine="exact"):
     """-> (loss_rows[M], lse[M], dq[M, D] or None); see include/pcv_b200.h."""
     Q, targets = _f32(Q, "Q"), _i64(targets, "targets").reshape(-1)
     M, D = Q.shape
@@ -354,6 +355,7 @@ def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0,
         mask.bitmask = bitmask.data_ptr()
     mask.seed, mask.offset = int(seed), int(offset)
     mask.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
+    mask.engine = 1 if engine == "tf32" else 0
     loss = torch.empty(M, dtype=torch.float32, device=Q.device)
     lse = torch.empty(M, dtype=torch.float32, device=Q.device)
     dq = torch.empty(M, D, dtype=torch.float32, device=Q.device) if want_dq else None

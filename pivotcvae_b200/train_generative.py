@@ -64,7 +64,7 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
     if bitmask is None and keep < 1.0:
         kw = model.noise.stream_args(M)
     recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, kw["seed"],
-                                      kw["offset"], kw.get("offset_dev"))
+                                      kw["offset"], kw.get("offset_dev"), getattr(model, "ce_engine", "exact"))
     KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
     loss = recLoss + beta * KLD
     return loss, recLoss, KLD

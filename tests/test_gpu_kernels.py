@@ -269,3 +269,22 @@ def test_errors_are_loud(ops):
     before = ops.launch_count()
     ops.score_select(tab, torch.zeros(4, 8, device=dev()))
     assert ops.launch_count() >= before + 2
+
+
+@pytest.mark.parametrize("n_items,M", [(2048, 128), (5000, 130), (100000, 300), (40001, 1000)])
+def test_ce_tensor_core_engine(ops, n_items, M):
+    """Opt-in tf32 engine of the dense catalog CE (logits on tcgen05): reduced-precision tolerance
+    (north_star: 1e-2; observed ~1e-4 on the loss, ~1e-3 on dq)."""
+    rng = np.random.default_rng(n_items + M)
+    W = rng.standard_normal((n_items, 8)).astype(np.float32)
+    W /= np.linalg.norm(W, axis=1, keepdims=True)
+    Q = rng.standard_normal((M, 8)).astype(np.float32) * rng.uniform(0.2, 1.0, (M, 1)).astype(np.float32)
+    tg = rng.integers(0, n_items, M)
+    tab = ops.Table(T(W))
+    loss, lse, dq = ops.ce_fwd_bwd(tab, T(Q), T(tg), 1.0, engine="tf32")
+    rl, rlse, rdq = oracle.ce(W, Q, tg, None)
+    np.testing.assert_allclose(N(loss), rl, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(N(lse), rlse, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(N(dq), rdq, rtol=1e-2, atol=1e-3)
+    el, _, edq = ops.ce_fwd_bwd(tab, T(Q), T(tg), 1.0, engine="exact")
+    np.testing.assert_allclose(N(loss), N(el), rtol=1e-3, atol=1e-3)

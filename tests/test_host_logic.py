@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     from pivotcvae_b200 import _lib
     lib = _lib.load()           # loads without a GPU; no compute call is made here
     names = _header_functions()
-    assert len(names) >= 19
+    assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "libpcv_b200.so does not export %s" % n
         assert n in _lib.EXPORTS, "%s is declared in the header but has no ctypes prototype" % n
@@ -43,7 +43,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
               "pcv_segment": (_lib.Segment, ["kind", "ptr", "idx", "width", "count", "norm"]),
               "pcv_mlp_desc": (_lib.MlpDesc, ["n_segments", "seg", "n_layers", "layer", "out", "out_ld", "out_col0",
                                               "copy_seg", "x0", "acts", "latent", "eps", "seed", "offset", "z", "eps_out", "offset_dev"]),
-              "pcv_ce_mask": (_lib.CeMask, ["keep_prob", "bitmask", "seed", "offset", "offset_dev"]),
+              "pcv_ce_mask": (_lib.CeMask, ["keep_prob", "bitmask", "seed", "offset", "offset_dev", "engine"]),
               "pcv_urm_desc": (_lib.UrmDesc, ["variant", "doc_table", "user_table", "item_bias", "user_bias", "pos_bias",
                                               "pos_dep", "mr_factor", "L", "D"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pcv_b200.h"', "int main(void){"]
