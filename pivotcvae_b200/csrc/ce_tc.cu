@@ -31,6 +31,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// explicit shared-space 128-bit load (a generic-pointer load would go through the global LSU path)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32]) {
   float g[11];
 #pragma unroll
@@ -162,7 +169,7 @@ ce_tc_kernel(const float *__restrict__ Wsw, int64_t n_rows, const float *__restr
       int cnt = 0;
 
       // one chunk of 32 logits: rescale on a new maximum (rare), then 32 x (ex2, l +=, 8 FFMA)
-      auto process = [&](uint32_t (&v)[32], const float *tile, int col0, int lim) {
+      auto process = [&](uint32_t (&v)[32], uint32_t tile, int col0, int lim) {
         const float cm = chunk_max32(v);
         if (cm > m) {
           const float sc = ex2_approx((m - cm) * LOG2E);
@@ -179,8 +186,8 @@ ce_tc_kernel(const float *__restrict__ Wsw, int64_t n_rows, const float *__restr
           l += p;
           const int j = col0 + i;                       // row of the tile (compile-time offset within the slice)
           const int sw = (j >> 2) & 1;
-          const float4 w0 = *reinterpret_cast<const float4 *>(tile + j * TC_D + ((0 ^ sw) << 2));
-          const float4 w1 = *reinterpret_cast<const float4 *>(tile + j * TC_D + ((1 ^ sw) << 2));
+          const float4 w0 = lds128(tile + (uint32_t)(j * TC_D + ((0 ^ sw) << 2)) * 4u);
+          const float4 w1 = lds128(tile + (uint32_t)(j * TC_D + ((1 ^ sw) << 2)) * 4u);
           acc[0] = fmaf(p, w0.x, acc[0]); acc[1] = fmaf(p, w0.y, acc[1]); acc[2] = fmaf(p, w0.z, acc[2]);
           acc[3] = fmaf(p, w0.w, acc[3]); acc[4] = fmaf(p, w1.x, acc[4]); acc[5] = fmaf(p, w1.y, acc[5]);
           acc[6] = fmaf(p, w1.z, acc[6]); acc[7] = fmaf(p, w1.w, acc[7]);
@@ -198,19 +205,17 @@ ce_tc_kernel(const float *__restrict__ Wsw, int64_t n_rows, const float *__restr
         const int n_valid = (int)max((int64_t)0, min((int64_t)TC_SW, j_end - tile_j0));
         cnt += n_valid;
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * TC_SW);
-        const float *tile = S.b[s] + slice * TC_SW * TC_D;
-        uint32_t va[32], vb[32];
+        const uint32_t tile = smem_u32(S.b[s] + slice * TC_SW * TC_D);
+        uint32_t va[32];
         TC_LD32(va, taddr);
         TC_WAIT_LD(va);
         if (n_valid == TC_SW) {
-#pragma unroll
-          for (int c = 0; c < NCH; c += 2) {
-            TC_LD32(vb, taddr + (c + 1) * 32);
-            process(va, tile, c * 32, 32);
-            TC_WAIT_LD(vb);
-            if (c + 2 < NCH) TC_LD32(va, taddr + (c + 2) * 32);
-            process(vb, tile, (c + 1) * 32, 32);
-            if (c + 2 < NCH) TC_WAIT_LD(va);
+          // (one register buffer: the math of a chunk is ~40x its TMEM load, two warps per scheduler hide it;
+          //  a second buffer pushed the kernel into local-memory spills)
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            if (c > 0) { TC_LD32(va, taddr + c * 32); TC_WAIT_LD(va); }
+            process(va, tile + (uint32_t)(c * 32 * TC_D * 4), 0, 32);
           }
         } else {
 #pragma unroll 1
@@ -219,7 +224,7 @@ ce_tc_kernel(const float *__restrict__ Wsw, int64_t n_rows, const float *__restr
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= n_valid) va[i] = 0xff800000u;   // -inf: e^{-inf} = 0, stale rows contribute nothing
-            if (c * 32 < n_valid) process(va, tile, c * 32, min(32, n_valid - c * 32));
+            if (c * 32 < n_valid) process(va, tile + (uint32_t)(c * 32 * TC_D * 4), 0, min(32, n_valid - c * 32));
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
