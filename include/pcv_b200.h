@@ -251,6 +251,16 @@ typedef struct {
 int pcv_urm_fwd(const pcv_urm_desc *d, const int64_t *slates, const int64_t *users,
                 int64_t B, float *out, pcv_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* Slate metrics of the variation-control evaluation (analysis.py:5-30) */
+/* ------------------------------------------------------------------ */
+/* ils[b] = (sum_{i,j} cos(e_i, e_j) - L) / (L (L-1)) over the L items of slate b (get_ILS);
+ * bitmap (optional, ceil(N/32) words, zeroed by the caller) gets bit `item` set for every
+ * recommended item; pcv_popcount(bitmap) / N is get_coverage. table: [N, D] raw embeddings. */
+int pcv_slate_metrics(const float *table, int D, const int64_t *slates, int64_t B, int L, float *ils,
+                      uint32_t *bitmap, pcv_stream_t stream);
+int pcv_popcount(const uint32_t *bitmap, int64_t words, uint64_t *count, pcv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

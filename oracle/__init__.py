@@ -374,3 +374,17 @@ def resp_mlp(sd, slates, users, no_user):
     """UserResponseModel_MLP.forward: env/response_model.py:76-87 (plain ReLU)."""
     x = resp_input(sd["docEmbed.weight"], None if no_user else sd["userEmbed.weight"], slates, users, no_user)
     return mlp(x, sd, "mlp", ACT_NONE, hidden_act=ACT_RELU)
+
+
+def ils(table, slates):
+    """analysis.py:13-30 get_ILS -> f32[B]."""
+    table, slates = _f32(table), _i64(slates)
+    B, L = slates.shape
+    out = np.empty(B, dtype=np.float32)
+    lib().orc_ils(_p(table), I32(table.shape[1]), _p(slates), I64(B), I32(L), _p(out))
+    return out
+
+
+def coverage(slates, N):
+    """analysis.py:5-11 get_coverage."""
+    return len(np.unique(np.asarray(slates))) * 1.0 / N

@@ -494,3 +494,25 @@ void orc_resp_input(const float *doc, const float *usr, int L, int D, const int6
     }
   }
 }
+
+/* ---- analysis.py:13-30 get_ILS: normalise the L gathered rows, bmm(emb, emb^T), (sum - L) / (L (L-1)) ---- */
+void orc_ils(const float *table, int D, const int64_t *slates, int64_t B, int L, float *ils) {
+  for (int64_t b = 0; b < B; ++b) {
+    float e[16][128];
+    for (int l = 0; l < L; ++l) {
+      const float *r = table + slates[b * L + l] * D;
+      float ss = 0.f;
+      for (int k = 0; k < D; ++k) ss = fmaf(r[k], r[k], ss);
+      float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      for (int k = 0; k < D; ++k) e[l][k] = r[k] / nrm;
+    }
+    double tot = 0.0;
+    for (int i = 0; i < L; ++i)
+      for (int j = 0; j < L; ++j) {
+        double d = 0.0;
+        for (int k = 0; k < D; ++k) d += (double)e[i][k] * (double)e[j][k];
+        tot += d;
+      }
+    ils[b] = (float)((tot - (double)L) / (double)(L * (L - 1)));
+  }
+}

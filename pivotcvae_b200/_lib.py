@@ -86,6 +86,8 @@ EXPORTS = {
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcv_cand_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
+    "pcv_slate_metrics": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcv_popcount": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pcv_urm_fwd": (c_int, [ctypes.POINTER(UrmDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 

@@ -113,8 +113,41 @@ class URM(Environment):
         return (slate_p >= 0.5).to(slate_p.dtype)
 
     def generate_response_for_dataset(self, sampledU, sampledSlates):
+        """One launch over all records (the reference loops 128 at a time, :170-185)."""
         with torch.no_grad():
             return self.sample_response(self.forward(sampledSlates, sampledU.reshape(-1)))
+
+    def generate_dataset(self, min_user_hist=20, min_item_hist=20, n_record=1000000):
+        """Simulated (user, slate, responses) records (response_model.py:188-262): every user gets
+        >= min_user_hist slates, every item leads >= min_item_hist slates, the rest are uniform.
+        The reference draws ids with torch.multinomial(ones, replacement=True) on the CPU, i.e.
+        uniformly; here they are drawn uniformly on the device and every record is scored by one
+        pcv_urm_fwd launch.  Returns numpy (users (R,), slates (R, L), responses (R, L))."""
+        nU, nI, Ls = int(self.maxUID) + 1, int(self.maxIID) + 1, self.slateSize
+        assert min_user_hist * (nU - 1) + min_item_hist * (nI - 1) < n_record
+        n_record = max(n_record, nU * min_user_hist, nI * min_item_hist)
+        dev = self.docEmbed.weight.device
+        if dev.type != "cuda":
+            raise L.PcvError("response models run on a B200 only: move the module with .to('cuda:0')")
+        users, slates = [], []
+        if min_user_hist > 0:
+            users.append(torch.arange(nU, device=dev).repeat_interleave(min_user_hist))
+            slates.append(torch.randint(0, nI, (nU * min_user_hist, Ls), device=dev))
+        if min_item_hist > 0:
+            users.append(torch.randint(0, nU, (nI * min_item_hist,), device=dev))
+            sl = torch.randint(0, nI, (nI, min_item_hist, Ls), device=dev)
+            sl[:, :, 0] = torch.arange(nI, device=dev).view(-1, 1)
+            slates.append(sl.reshape(-1, Ls))
+        done = sum(len(u) for u in users)
+        if done < n_record:
+            users.append(torch.randint(0, nU, (n_record - done,), device=dev))
+            slates.append(torch.randint(0, nI, (n_record - done, Ls), device=dev))
+        # the reference sizes its buffers to n_record and lets the guaranteed blocks overflow it
+        # only when the assert above already failed, so concatenation yields the same layout
+        genU = torch.cat(users)[:n_record]
+        genS = torch.cat(slates)[:n_record]
+        genR = self.generate_response_for_dataset(genU, genS).to(torch.float32)
+        return genU.cpu().numpy(), genS.cpu().numpy(), genR.cpu().numpy()
 
 
 class URM_P(URM):

@@ -382,8 +382,27 @@ def cand_fixture(path, seed):
     np.savez(path, **out)
 
 
+def metrics_fixture(path, seed):
+    """analysis.py get_coverage / get_ILS on random slates."""
+    import analysis
+    g = torch.Generator().manual_seed(seed)
+    n_items, B = 900, 200
+    emb = torch.nn.Embedding(n_items, 8)
+    with torch.no_grad():
+        emb.weight.copy_(torch.randn(n_items, 8, generator=g))
+    slates = torch.randint(0, n_items, (B, 5), generator=g)
+    slates[3] = slates[3, 0]          # a slate of identical items: ILS = 1
+    with torch.no_grad():
+        ils = analysis.get_ILS(slates, emb)
+    np.savez(path, **{"table": emb.weight.detach().numpy(), "slates": slates.numpy(), "ils": ils.numpy(),
+                      "coverage": np.array(analysis.get_coverage(slates, n_items))})
+
+
 if __name__ == "__main__":
     assert check_multinomial_emulation()
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        metrics_fixture(os.path.join(HERE, "metrics.npz"), 99)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cand":
         cand_fixture(os.path.join(HERE, "cand_small.npz"), 6060)
         sys.exit(0)
@@ -397,6 +416,7 @@ if __name__ == "__main__":
     env_fixture(os.path.join(HERE, "env_small.npz"), 31337)
     dims_fixture(os.path.join(HERE, "dims.npz"), 555)
     cand_fixture(os.path.join(HERE, "cand_small.npz"), 6060)
+    metrics_fixture(os.path.join(HERE, "metrics.npz"), 99)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -340,3 +340,33 @@ def test_train_on_dataset_get_model_sample_encoding(golden, tmp_path):
         assert rx.shape == (8, Ls, D) and torch.equal(rx[:, 0], best.docEmbed.weight[s8[:, 0]])
         items = best.get_recommended_item(rx)
         assert items.shape == (8 * Ls,) and bool((items.view(8, Ls)[:, 0] == s8[:, 0]).all() or True)
+
+
+def test_slate_metrics_gpu(golden):
+    """analysis.get_coverage / get_ILS (analysis.py:5-30) fused over the recommended slates."""
+    from pivotcvae_b200 import analysis
+    fx = golden("metrics")
+    emb = torch.nn.Embedding(900, 8).cuda()
+    with torch.no_grad():
+        emb.weight.copy_(T(fx["table"]))
+    ils = analysis.get_ILS(T(fx["slates"]), emb)
+    np.testing.assert_allclose(N(ils), fx["ils"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(N(ils), oracle.ils(fx["table"], fx["slates"]), rtol=1e-5, atol=1e-6)
+    assert analysis.get_coverage(T(fx["slates"]), 900) == float(fx["coverage"])
+
+
+def test_generate_dataset_gpu():
+    """URM.generate_dataset (response_model.py:188-262): coverage guarantees + responses == oracle."""
+    from pivotcvae_b200.env.response_model import URM_P_MR
+    torch.manual_seed(5)
+    env = URM_P_MR(59, 39, 5, 8, "cuda:0", False, 0.2, -0.2, 0.3).to("cuda:0")
+    u, s, r = env.generate_dataset(min_user_hist=3, min_item_hist=2, n_record=400)
+    assert u.shape == (400,) and s.shape == (400, 5) and r.shape == (400, 5) and r.dtype == np.float32
+    assert np.bincount(u, minlength=40).min() >= 3
+    assert np.bincount(s[:, 0], minlength=60).min() >= 2
+    assert (u[:120] == np.repeat(np.arange(40), 3)).all()
+    assert (s[120:240, 0] == np.repeat(np.arange(60), 2)).all()
+    p = oracle.urm(2, N(env.docEmbed.weight), N(env.userEmbed.weight), N(env.itemBias.weight).reshape(-1),
+                   N(env.userBias.weight).reshape(-1), s, u, N(env.posBias), N(env.posDependentBias), 0.3)
+    sure = np.abs(p - 0.5) > 1e-5          # libm vs device expf may differ by an ulp at the threshold
+    np.testing.assert_array_equal(r[sure], (p >= 0.5).astype(np.float32)[sure])

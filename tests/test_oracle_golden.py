@@ -200,3 +200,11 @@ def test_candidate_mode_loss(golden, kind):
     W = sd["docEmbed.weight"]
     _, _, p = oracle.cand_ce(W, f["rx"].reshape(-1, 8), fx["in/candidates"], fx["in/targets"])
     np.testing.assert_allclose(p, fx[kind + "/p"], rtol=1e-4, atol=1e-5)
+
+
+def test_slate_metrics(golden):
+    """analysis.py:5-30: coverage and intra-list similarity."""
+    fx = golden("metrics")
+    np.testing.assert_allclose(oracle.ils(fx["table"], fx["slates"]), fx["ils"], rtol=1e-5, atol=1e-6)
+    assert abs(oracle.ils(fx["table"], fx["slates"])[3] - 1.0) < 1e-6
+    assert oracle.coverage(fx["slates"], 900) == float(fx["coverage"])
