@@ -13,7 +13,7 @@
 //   2. One elected thread issues tcgen05.mma.kind::tf32, M=128 (query rows, staged
 //      once per CTA), N=256, K=8 per tile; accumulators ping-pong between two
 //      256-column TMEM buffers (512 columns = all of TMEM).
-//   3. TC_EPI_WARPS epilogue warps read their TMEM lanes (tcgen05.ld 32x32b.x32: thread =
+//   3. SEL_EPI_WARPS epilogue warps read their TMEM lanes (tcgen05.ld 32x32b.x32: thread =
 //      query row), keep a running max r of the APPROXIMATE scores and record every
 //      32-item chunk whose approximate maximum is >= r - band in a per-row
 //      shared-memory list (fast path: 16 FMNMX3 + 1 compare per 32 logits).
@@ -33,15 +33,34 @@
 
 namespace pcv {
 
-constexpr int TC_CAP = 32 / TC_SLICES;               // in-kernel recorded-chunk list capacity per (slice, row)
+// Optional phase trace of CTA 0 (profiles/trace_select.py builds a separate library with -DPCV_TC_TRACE).
+#ifdef PCV_TC_TRACE
+__device__ long long g_tc_trace[16];
+__device__ long long g_tc_cta[4][256];   // per CTA: clock64 at entry / exit, globaltimer at entry / exit
+__device__ __forceinline__ long long tc_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_TRACE(i) do { if (blockIdx.x == 0) g_tc_trace[i] = clock64();                                          \
+    if ((i) == 0) { g_tc_cta[0][blockIdx.x & 255] = clock64(); g_tc_cta[2][blockIdx.x & 255] = tc_gtime(); }      \
+    if ((i) == 14) { g_tc_cta[1][blockIdx.x & 255] = clock64(); g_tc_cta[3][blockIdx.x & 255] = tc_gtime(); } } while (0)
+#else
+#define TC_TRACE(i) do { } while (0)
+#endif
+
+// The epilogue is latency-bound per warp (TMEM load -> max tree -> compare -> branch), so it runs
+// 16 warps: four per TMEM lane quarter, each owning a 64-column slice of every 256-column tile.
+constexpr int SEL_EPI_WARPS = 16;                     // multiple of 4 (a warp reads one TMEM lane quarter)
+constexpr int SEL_SLICES = SEL_EPI_WARPS / 4;         // column slices of a tile
+constexpr int SEL_SW = TC_BN / SEL_SLICES;            // columns per slice
+constexpr int SEL_THREADS = 64 + 32 * SEL_EPI_WARPS;  // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
+constexpr int SEL_STAGES = 12;                        // 8 KB table tiles in flight
+constexpr int TC_CAP = 16;                            // in-kernel recorded-chunk list capacity per (slice, row)
 constexpr int TC_OUT = 8;                            // recorded chunks handed to the refine kernel per (stream, row)
 
 struct __align__(1024) TcSmem {
-  float b[TC_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
+  float b[SEL_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
   float a[2][TC_BM * TC_D];                    // query tiles (double-buffered across work items), same layout
-  unsigned long long cand[TC_SLICES][TC_CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
+  unsigned long long cand[SEL_SLICES][TC_CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
   float rmax[TC_BM];                           // running max per row, shared by the column slices
-  unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2], afull[2], aempty[2];
+  unsigned long long full[SEL_STAGES], empty[SEL_STAGES], tfull[2], tempty[2], afull[2], aempty[2];
   uint32_t tmem_base;
 };
 
@@ -56,16 +75,26 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[1
   return max3(max3(a, b, c), g[9], g[10]);
 }
 
-// PERSISTENT: one CTA per SM loops over work items (row tile, catalog split); TMEM, the mbarrier
-// rings and the TMA pipeline live across items, so the per-item cost is just the tile stream
-// (matters for small catalogs, where an item is only ~18 tiles).  Roles:
+// Work decomposition: the (row tile, table tile) pairs form one flat sequence of n_units =
+// row_tiles * T units (T = table tiles per row tile); CTA c of G owns the contiguous units
+// [c*n_units/G, (c+1)*n_units/G) and cuts them at row-tile boundaries into SEGMENTS
+// (row tile, [ct0, ct1)).  A row tile is therefore touched by a handful of consecutive CTAs
+// (<= ceil(T / (n_units/G)) + 1): its "slots", numbered from the first CTA that touches it.
+__host__ __device__ __forceinline__ int64_t tc_cta_begin(int64_t c, int64_t n_units, int G) { return c * n_units / G; }
+// the CTA that owns unit x: the largest c with tc_cta_begin(c) <= x
+__host__ __device__ __forceinline__ int tc_cta_of(int64_t x, int64_t n_units, int G) {
+  return (int)(((x + 1) * G - 1) / n_units);
+}
+
+// PERSISTENT: one CTA per SM walks its segments; TMEM, the mbarrier rings and the TMA pipeline
+// live across segments, so the per-segment cost is just the tile stream.  Roles:
 //   warp 0  : stages the NEXT item's 128 query rows into the double-buffered A tile (all lanes),
 //             then lane 0 streams that item's table tiles with TMA bulk copies;
 //   warp 1  : lane 0 issues one tcgen05.mma per tile (TMEM alloc/dealloc by the whole warp);
 //   warps 2+: epilogue (thread = query row x column slice).
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(SEL_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
-                       const float *__restrict__ Q, int64_t M, int64_t items_per_split, int n_split, int n_work,
+                       const float *__restrict__ Q, int64_t M, int T, int64_t n_units,
                        float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
                        unsigned long long *__restrict__ out_ent, unsigned int *__restrict__ ovf_count,
                        unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cap) {
@@ -73,11 +102,12 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_TRACE(0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < SEL_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], TC_EPI_WARPS);
+      mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], SEL_EPI_WARPS);
       mbar_init(&S.afull[b], 1); mbar_init(&S.aempty[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,28 +120,31 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
+  if (threadIdx.x == 0) TC_TRACE(1);
 
-  // work item w -> (row tile, split); consecutive items of a CTA walk the splits of nearby row tiles
-  // each CTA owns a CONTIGUOUS range of work items, so the splits of one row tile are mostly
-  // visited back to back by the same CTA and the rows' running maxima carry over between them
-  const int w_begin = (int)((int64_t)blockIdx.x * n_work / gridDim.x);
-  const int w_end = (int)((int64_t)(blockIdx.x + 1) * n_work / gridDim.x);
-  auto item_rows = [&](int w) { return (int64_t)(w / n_split) * TC_BM; };
-  // the splits of a row tile are visited in an order rotated by the tile index, so concurrent
-  // CTAs (which mostly hold different row tiles) stream different parts of the table
-  auto item_split = [&](int w) { return (w % n_split + (w / n_split) * 3) % n_split; };
-  auto item_jb = [&](int w) { return (int64_t)item_split(w) * items_per_split; };
+  const int64_t u_begin = tc_cta_begin(blockIdx.x, n_units, gridDim.x);
+  const int64_t u_end = tc_cta_begin(blockIdx.x + 1, n_units, gridDim.x);
+  // segment starting at unit u: row tile rt, table tiles [ct0, ct0 + n_tiles)
+#define TC_SEGMENT(u)                                                            \
+  const int rt = (int)((u) / T);                                                 \
+  const int ct0 = (int)((u) - (int64_t)rt * T);                                  \
+  const int n_tiles = (int)min((int64_t)(T - ct0), u_end - (u));                 \
+  const int64_t j_begin = (int64_t)ct0 * TC_BN;                                  \
+  const int64_t j_end = min(n_rows, (int64_t)(ct0 + n_tiles) * TC_BN);
 
   if (warp == 0) {
     // ---------------- producer: A tile of the item, then its table tiles ----------------
     uint32_t gt = 0;   // tiles issued so far (ring position)
     int it = 0;        // items started so far
-    for (int w = w_begin; w < w_end; ++w, ++it) {
+    for (int64_t u = u_begin; u < u_end; ++it) {
+      TC_SEGMENT(u)
+      u += n_tiles;
+      (void)j_end;
       const int ab = it & 1;
-      mbar_wait(&S.aempty[ab], ((it >> 1) & 1) ^ 1);   // MMAs of the item that used this A buffer are done
+      mbar_wait(&S.aempty[ab], ((it >> 1) & 1) ^ 1);   // MMAs of the segment that used this A buffer are done
       {
         // 128 query rows: row t at byte t*32, 16-byte chunk c at ((c ^ bit2(t)) * 16)  (SWIZZLE_32B image)
-        const int64_t row_base = item_rows(w);
+        const int64_t row_base = (int64_t)rt * TC_BM;
 #pragma unroll
         for (int i = 0; i < TC_BM / 32; ++i) {
           const int t = lane + 32 * i;
@@ -129,19 +162,18 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.afull[ab]);
+        if (lane == 0 && it == 0) TC_TRACE(2);
       }
       if (lane == 0) {
-        const int64_t j_begin = item_jb(w);
-        const int64_t j_end = min(n_rows, j_begin + items_per_split);
-        const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
         for (int t = 0; t < n_tiles; ++t, ++gt) {
-          const int s = gt % TC_STAGES;
-          const uint32_t ph = (gt / TC_STAGES) & 1;
+          const int s = gt % SEL_STAGES;
+          const uint32_t ph = (gt / SEL_STAGES) & 1;
           mbar_wait(&S.empty[s], ph ^ 1);
           const int64_t j0 = j_begin + (int64_t)t * TC_BN;
           const uint32_t bytes = (uint32_t)min((int64_t)TC_TILE_BYTES, (n_rows - j0) * (int64_t)(TC_D * 4));
           mbar_expect_tx(&S.full[s], bytes);  // rows past the end of the table keep stale data: masked below
           tma_bulk_load(S.b[s], Wsw + j0 * TC_D, bytes, &S.full[s]);
+          if (gt == 0) TC_TRACE(3);
         }
       }
       __syncwarp();
@@ -151,21 +183,22 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
     if (lane == 0) {
       uint32_t gt = 0;
       int it = 0;
-      for (int w = w_begin; w < w_end; ++w, ++it) {
+      for (int64_t u = u_begin; u < u_end; ++it) {
+        TC_SEGMENT(u)
+        u += n_tiles;
+        (void)j_begin; (void)j_end;
         const int ab = it & 1;
-        const int64_t j_begin = item_jb(w);
-        const int64_t j_end = min(n_rows, j_begin + items_per_split);
-        const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
         mbar_wait(&S.afull[ab], (it >> 1) & 1);
         const uint64_t adesc = umma_desc_sw32(S.a[ab]);
         for (int t = 0; t < n_tiles; ++t, ++gt) {
-          const int s = gt % TC_STAGES;
-          const uint32_t ph = (gt / TC_STAGES) & 1;
+          const int s = gt % SEL_STAGES;
+          const uint32_t ph = (gt / SEL_STAGES) & 1;
           const int buf = gt & 1;
           const uint32_t bph = (gt >> 1) & 1;
           mbar_wait(&S.tempty[buf], bph ^ 1);
           mbar_wait(&S.full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (gt == 0) TC_TRACE(4);
           umma_tf32(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC, 0);
           umma_commit(&S.empty[s]);
           umma_commit(&S.tfull[buf]);
@@ -176,20 +209,17 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   } else {
     // ---------------- epilogue: thread = (query row, column slice) ----------------
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read
-    const int slice = (warp - 2) >> 2;        // which TC_SW columns of every 256-column tile
+    const int slice = (warp - 2) >> 2;        // which SEL_SW columns of every 256-column tile
     const int trow = quarter * 32 + lane;
     unsigned long long *list = &S.cand[slice][0][trow];  // entry e at list[e * TC_BM]
     uint32_t gt = 0;
-    int prev_tile = -1;
-    float r = 0.f, thr = 0.f, band = 0.f;   // per-row state, carried across the splits of a row tile
-    for (int w = w_begin; w < w_end; ++w) {
-      const int64_t row = item_rows(w) + trow;
-      const int64_t j_begin = item_jb(w);
-      const int64_t j_end = min(n_rows, j_begin + items_per_split);
-      const int n_tiles = (int)((j_end - j_begin + TC_BN - 1) / TC_BN);
+    float r = 0.f, thr = 0.f, band = 0.f;   // per-row state of the current segment
+    for (int64_t u = u_begin; u < u_end;) {
+      TC_SEGMENT(u)
+      u += n_tiles;
+      const int64_t row = (int64_t)rt * TC_BM + trow;
       const bool live = row < M;
-      if (w / n_split != prev_tile) {   // new rows: reset the running max (any earlier maximum of the SAME row stays valid)
-        prev_tile = w / n_split;
+      {   // every segment starts on new rows: reset the running max
         float ss = 0.f;
         if (live) {
           const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
@@ -247,26 +277,30 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
           if (col0 + i >= n_valid) v[i] = 0xff800000u;  // -inf: stale / foreign columns never win
       };
 
-      constexpr int NCH = TC_SW / 32;  // chunks per slice per tile (even)
+      constexpr int NCH = SEL_SW / 32;  // chunks per slice per tile (even)
       for (int t = 0; t < n_tiles; ++t, ++gt) {
         const int buf = gt & 1;
         const uint32_t bph = (gt >> 1) & 1;
         mbar_wait(&S.tfull[buf], bph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * TC_SW;
-        const int n_valid = (int)min((int64_t)TC_SW, j_end - tile_j0);  // may be <= 0
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * TC_SW);
+        if (threadIdx.x == 64 && gt < 8) TC_TRACE(5 + gt);
+        const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * SEL_SW;
+        const int n_valid = (int)min((int64_t)SEL_SW, j_end - tile_j0);  // may be <= 0
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * SEL_SW);
         const int32_t jb0 = (int32_t)tile_j0;
         uint32_t va[32], vb[32];
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
         TC_LD32(va, taddr);
-        if (live && t < 4) {   // (first tiles of an item, while the TMEM load is in flight) exchange the running max with the other column slice
+        // (first tiles of a long segment, while the TMEM load is in flight) exchange the running max with the
+        // other column slice.  The slices are never more than the two TMEM buffers apart, so with >= 8 tiles
+        // per exchanging segment a slice can not read a value the other one published for a LATER segment.
+        if (live && t < 4 && n_tiles >= 8) {
           const float sh = S.rmax[trow];
           if (sh > r) { r = sh; thr = r - band; }
           else if (r > sh) S.rmax[trow] = r;
         }
         TC_WAIT_LD(va);
-        if (n_valid == TC_SW) {
+        if (n_valid == SEL_SW) {
 #pragma unroll
           for (int c = 0; c < NCH; c += 2) {
             TC_LD32(vb, taddr + (c + 1) * 32);
@@ -289,8 +323,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         if (lane == 0) mbar_arrive(&S.tempty[buf]);
       }
       if (live) {
-        // hand the surviving chunks of this (split, slice) stream to the refine kernel
-        const int64_t stream = (int64_t)item_split(w) * TC_SLICES + slice;
+        // hand the surviving chunks of this (slot, slice) stream to the refine kernel
+        const int64_t stream = (int64_t)((int)blockIdx.x - tc_cta_of((int64_t)rt * T, n_units, gridDim.x)) * SEL_SLICES + slice;
         int k = 0;
         for (int e = 0; e < cnt; ++e) {
           const unsigned long long ent = list[e * TC_BM];
@@ -303,16 +337,28 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         out_r[stream * M + row] = r;
         out_cnt[stream * M + row] = ovf ? -1 : min(k, TC_OUT);
       }
+      if (threadIdx.x == 64) TC_TRACE(13);
     }
   }
 
+#undef TC_SEGMENT
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    if (lane == 0) TC_TRACE(14);
   }
 }
+
+#ifdef PCV_TC_TRACE
+extern "C" int pcv_debug_tc_trace(long long *host16) {
+  return (int)cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(long long) * 16);
+}
+extern "C" int pcv_debug_tc_cta(long long *host4x256) {
+  return (int)cudaMemcpyFromSymbol(host4x256, g_tc_cta, sizeof(long long) * 4 * 256);
+}
+#endif
 
 // Exact re-score of the chunks that did not fit the per-stream lists: one warp per entry
 // (lane = item); the exact winner is merged into row_best[row] with a packed 64-bit atomicMax:
@@ -371,7 +417,7 @@ tc_overflow_kernel(const float *__restrict__ W, int64_t n_rows, const float *__r
 // inside the band, i.e. heavy exact ties) are scanned completely.
 __global__ void __launch_bounds__(256)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
-                 int64_t M, int n_split, int64_t items_per_split, float band_scale,
+                 int64_t M, int T, int64_t n_units, int G, float band_scale,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
                  const unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                  unsigned int *__restrict__ ovf_count_reset, int64_t *__restrict__ out_idx,
@@ -379,7 +425,28 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  const int n_streams = n_split * TC_SLICES;
+  // the streams of this row: (slot, slice) for the CTAs cfirst..clast that touched its row tile
+  const int64_t rt = row / TC_BM;
+  const int cfirst = tc_cta_of(rt * T, n_units, G);
+  const int clast = tc_cta_of((rt + 1) * T - 1, n_units, G);
+  const int n_streams = (clast - cfirst + 1) * SEL_SLICES;
+  // every load that does not depend on another one is issued up front (one memory latency)
+  auto load_group = [&](int base, int &cnt, unsigned long long (&ents)[TC_OUT]) {
+    const int s = base + lane;
+    cnt = 0;
+#pragma unroll
+    for (int e = 0; e < TC_OUT; ++e) ents[e] = 0ull;
+    if (s < n_streams) {
+      cnt = out_cnt[(int64_t)s * M + row];
+#pragma unroll
+      for (int e = 0; e < TC_OUT; ++e) ents[e] = out_ent[((int64_t)s * TC_OUT + e) * M + row];   // e >= cnt: stale, ignored
+    }
+  };
+  int cnt;
+  unsigned long long ents[TC_OUT];
+  float R = -INFINITY;
+  for (int s = lane; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
+  load_group(0, cnt, ents);
   float q[TC_D];
   {
     const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
@@ -390,8 +457,6 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
 #pragma unroll
   for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
   const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
-  float R = -INFINITY;
-  for (int s = lane; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
   R = warp_max(R);
   const float thr = R - band;
   float best = -INFINITY;
@@ -406,32 +471,29 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   };
   // lane = stream while the lists are inspected, lane = item while a chunk is re-scored
   for (int base = 0; base < n_streams; base += 32) {
-    const int s = base + lane;
-    const int cnt = (s < n_streams) ? out_cnt[(int64_t)s * M + row] : 0;
+    if (base > 0) load_group(base, cnt, ents);
     unsigned flagged = __ballot_sync(0xffffffffu, cnt < 0);
     while (flagged) {  // exact scan of a flagged stream's whole column range
       const int fs = base + __ffs(flagged) - 1;
       flagged &= flagged - 1;
-      const int split = fs / TC_SLICES, slice = fs % TC_SLICES;
-      const int64_t j_begin = (int64_t)split * items_per_split;
-      const int64_t j_end = min(n_rows, j_begin + items_per_split);
-      for (int64_t t0 = j_begin + slice * TC_SW; t0 < j_end; t0 += TC_BN)
-        for (int i = lane; i < TC_SW; i += 32)
+      const int slot = fs / SEL_SLICES, slice = fs % SEL_SLICES;
+      const int64_t c = cfirst + slot;
+      const int64_t tb = max(tc_cta_begin(c, n_units, G), rt * T) - rt * T;
+      const int64_t te = min(tc_cta_begin(c + 1, n_units, G), (rt + 1) * T) - rt * T;
+      const int64_t j_begin = tb * TC_BN;
+      const int64_t j_end = min(n_rows, te * TC_BN);
+      for (int64_t t0 = j_begin + slice * SEL_SW; t0 < j_end; t0 += TC_BN)
+        for (int i = lane; i < SEL_SW; i += 32)
           if (t0 + i < j_end) score(t0 + i);
     }
-#pragma unroll 1
+#pragma unroll
     for (int e = 0; e < TC_OUT; ++e) {
-      unsigned long long ent = 0;
-      bool pass = false;
-      if (e < cnt) {
-        ent = out_ent[((int64_t)s * TC_OUT + e) * M + row];
-        pass = __uint_as_float((uint32_t)(ent >> 32)) >= thr;
-      }
+      const bool pass = (e < cnt) && __uint_as_float((uint32_t)(ents[e] >> 32)) >= thr;
       unsigned live = __ballot_sync(0xffffffffu, pass);
       while (live) {
         const int src = __ffs(live) - 1;
         live &= live - 1;
-        const int64_t j = (int64_t)__shfl_sync(0xffffffffu, (uint32_t)ent, src) + lane;
+        const int64_t j = (int64_t)__shfl_sync(0xffffffffu, (uint32_t)ents[e], src) + lane;
         if (j < n_rows) score(j);
       }
     }
@@ -459,11 +521,12 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
 
 // ------------------------------------------------------------------ host side
 struct TcPlan {
-  int row_tiles, n_split;
+  int row_tiles, T, grid, slots;   // T = table tiles per row tile; slots = max CTAs touching one row tile
+  int64_t n_units;
   unsigned int ovf_cap;
-  int64_t items_per_split;
   int64_t rows_per_launch;   // rows handled per kernel triple; larger M is processed in groups
-  size_t ws_bytes;
+  size_t var_bytes;          // per-group part of the workspace (lists, overflow buffer)
+  size_t ws_bytes;           // 256 (counter) + rows_per_launch * 8 (row_best) + max var_bytes over the groups
 };
 
 constexpr size_t TC_WS_CAP = 192ull << 20;   // workspace budget: bigger problems are split into row groups
@@ -471,28 +534,24 @@ constexpr size_t TC_WS_CAP = 192ull << 20;   // workspace budget: bigger problem
 static void tc_plan_rows(const Table *t, int64_t M, TcPlan *p) {
   p->rows_per_launch = M;
   p->row_tiles = (int)((M + TC_BM - 1) / TC_BM);
-  const int64_t tiles = (t->n_rows + TC_BN - 1) / TC_BN;
-  int64_t max_split = tiles / 8;  // keep >= 8 tiles per CTA to amortise the prologue
-  if (max_split < 1) max_split = 1;
-  if (max_split > 64) max_split = 64;
-  int64_t best_ns = 1;
-  double best_eff = -1.0;
-  for (int64_t ns = 1; ns <= max_split; ++ns) {
-    const int64_t tps = (tiles + ns - 1) / ns;
-    const int64_t real_ns = (tiles + tps - 1) / tps;
-    const int64_t ctas = (int64_t)p->row_tiles * real_ns;
-    const int64_t waves = (ctas + t->sm_count - 1) / t->sm_count;
-    const double eff = (double)ctas / (double)(waves * t->sm_count);
-    if (eff > best_eff + 0.03) { best_eff = eff; best_ns = real_ns; }
+  p->T = (int)((t->n_rows + TC_BN - 1) / TC_BN);
+  p->n_units = (int64_t)p->row_tiles * p->T;
+  int64_t g = p->n_units / 8;   // keep >= 8 tiles per CTA to amortise the prologue
+  if (g < 1) g = 1;
+  if (g > t->sm_count) g = t->sm_count;
+  p->grid = (int)g;
+  int slots = 1;
+  for (int64_t rt = 0; rt < p->row_tiles; ++rt) {
+    const int n = tc_cta_of((rt + 1) * p->T - 1, p->n_units, p->grid) - tc_cta_of(rt * p->T, p->n_units, p->grid) + 1;
+    if (n > slots) slots = n;
   }
-  const int64_t tps = (tiles + best_ns - 1) / best_ns;
-  p->n_split = (int)((tiles + tps - 1) / tps);
-  p->items_per_split = tps * TC_BN;
+  p->slots = slots;
   // per (stream, row): running max (4) + count (4) + TC_OUT recorded chunks (8 each);
   // per row: packed overflow winner (8); overflow buffer: ovf_cap x (8 + 4) + counter
-  const size_t n_sr = (size_t)TC_SLICES * p->n_split * (size_t)M;
+  const size_t n_sr = (size_t)SEL_SLICES * p->slots * (size_t)M;
   p->ovf_cap = (unsigned int)(n_sr / 16 < 65536 ? 65536 : (n_sr / 16 > (1u << 24) ? (1u << 24) : n_sr / 16));
-  p->ws_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)M * 8 + (size_t)p->ovf_cap * 12 + 256;
+  p->var_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)p->ovf_cap * 12;
+  p->ws_bytes = 256 + (size_t)M * 8 + p->var_bytes;
 }
 
 static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
@@ -501,6 +560,11 @@ static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
   while (p->ws_bytes > TC_WS_CAP && mc > TC_BM) {   // halve the row group until the workspace fits the budget
     mc = ((mc + 1) / 2 + TC_BM - 1) / TC_BM * TC_BM;
     tc_plan_rows(t, mc, p);
+  }
+  if (M % mc) {   // the shorter last group has its own partition (more slots per row tile): size for both
+    TcPlan tail;
+    tc_plan_rows(t, M % mc, &tail);
+    if (tail.var_bytes > p->var_bytes) p->ws_bytes = 256 + (size_t)mc * 8 + tail.var_bytes;
   }
 }
 
@@ -563,14 +627,10 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     return PCV_ERR_WORKSPACE;
   }
   const int64_t Mg = p.rows_per_launch;                                // rows per group (== M when it fits)
-  const size_t n_sr = (size_t)TC_SLICES * p.n_split * (size_t)Mg;      // (stream, row) pairs of one group
-  unsigned long long *ent = reinterpret_cast<unsigned long long *>(ws);
-  unsigned long long *row_best = ent + n_sr * TC_OUT;                  // [Mg]   zeroed below
-  unsigned long long *ovf_ent = row_best + Mg;                         // [ovf_cap]
-  unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ovf_ent + p.ovf_cap);  // [2] zeroed below (counter + pad)
-  float *rr = reinterpret_cast<float *>(ovf_count + 2);
-  int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);
-  int32_t *ovf_row = cc + n_sr;
+  // fixed head (zero on entry, re-zeroed by tc_refine_kernel): overflow counter, per-row overflow winner
+  unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ws);
+  unsigned long long *row_best = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);   // [Mg]
+  unsigned long long *var = row_best + Mg;                             // per-group layout below
   const size_t smem = sizeof(TcSmem) + 1024;
   static bool attr_set[64] = {false};
   if (!attr_set[t->device & 63]) {
@@ -584,18 +644,24 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     const float *Qg = Q + r0 * TC_D;
     // row_best / ovf_count are zero on entry: the workspace must be zero-initialised ONCE by the caller
     // (see pcv_score_select_workspace_bytes) and tc_refine_kernel re-zeroes what a call dirtied
-    const int64_t n_work = ((m + TC_BM - 1) / TC_BM) * (int64_t)p.n_split;
-    const unsigned grid = (unsigned)(n_work < t->sm_count ? n_work : t->sm_count);   // persistent: <= one CTA per SM
-    score_select_tc_kernel<<<grid, TC_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, p.items_per_split,
-                                                           p.n_split, (int)n_work, band_scale, rr, cc, ent, ovf_count,
-                                                           ovf_ent, ovf_row, p.ovf_cap);
+    TcPlan g;   // the last group may be shorter: its own partition
+    tc_plan_rows(t, m, &g);
+    const size_t n_sr = (size_t)SEL_SLICES * g.slots * (size_t)m;       // (stream, row) pairs of this group
+    unsigned long long *ent = var;                                     // [n_sr][TC_OUT]
+    unsigned long long *ovf_ent = ent + n_sr * TC_OUT;                 // [ovf_cap]
+    float *rr = reinterpret_cast<float *>(ovf_ent + g.ovf_cap);        // [n_sr]
+    int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);              // [n_sr]
+    int32_t *ovf_row = cc + n_sr;                                      // [ovf_cap]
+    score_select_tc_kernel<<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.n_units,
+                                                                       band_scale, rr, cc, ent, ovf_count, ovf_ent,
+                                                                       ovf_row, g.ovf_cap);
     PCV_LAUNCH_CHECK();
-    tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Qg, ovf_count, ovf_ent, ovf_row, p.ovf_cap,
+    tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Qg, ovf_count, ovf_ent, ovf_row, g.ovf_cap,
                                                     row_best);
     PCV_LAUNCH_CHECK();
-    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, p.n_split,
-                                                             p.items_per_split, band_scale, rr, cc, ent, row_best,
-                                                             ovf_count, out_idx + r0, out_val ? out_val + r0 : nullptr);
+    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.n_units, g.grid,
+                                                             band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
+                                                             out_val ? out_val + r0 : nullptr);
     PCV_LAUNCH_CHECK();
   }
   return PCV_OK;
