@@ -125,6 +125,10 @@ typedef struct {
   const float *W; /* [n_out, n_in] row-major == nn.Linear.weight */
   const float *b; /* [n_out]                                     */
   int n_in, n_out, act;
+  /* optional: the same weights pre-tiled by pcv_mlp_pack (NULL = stream W as is).  When EVERY layer
+   * of a launch carries one, the TMA engine runs (one bulk copy per 32-k chunk, FMA-pipe-bound);
+   * results are bit-identical.  The caller re-packs after the weights change. */
+  const float *Wp;
 } pcv_linear;
 
 #define PCV_SEG_DENSE 0  /* ptr: float[B, width]                                      */
@@ -178,6 +182,10 @@ int pcv_mlp_fwd(const pcv_mlp_desc *d, int64_t B, pcv_stream_t stream);
 /* Two chained blocks in ONE launch: b may read (as DENSE segments) what a writes for the same
  * batch rows, e.g. prior -> reparameterise -> PSM (pivotcvae.py:279-291, 204-210). */
 int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_stream_t stream);
+/* Pre-tile one nn.Linear weight [n_out, n_in] for pcv_linear.Wp: `packed` (device, 128-byte aligned)
+ * holds pcv_mlp_packed_bytes(n_in, n_out) bytes. */
+size_t pcv_mlp_packed_bytes(int n_in, int n_out);
+int pcv_mlp_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream);
 
 /* KL(q || p) between diagonal Gaussians, summed over batch and latent
  * (train_generative.py:61) plus analytic grads (any grad pointer may be NULL).

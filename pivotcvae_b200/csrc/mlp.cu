@@ -21,6 +21,7 @@
 // nn.Linear's [n_out][n_in], prefetched one chunk ahead in registers); a thread
 // accumulates an 8-row x CT-column register tile.
 #include "pcv_common.cuh"
+#include "tc_common.cuh"   // mbarrier / TMA bulk-copy helpers
 
 namespace pcv {
 
@@ -55,6 +56,98 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t offset, int64_t 
   __sincosf(6.283185307179586f * pcv_u01(p.y), &s0, &c0);
   __sincosf(6.283185307179586f * pcv_u01(p.w), &s1, &c1);
   n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
+}
+
+// Prologue shared by both kernels: assemble x0 = [segments] into actA (transposed: element e of
+// row r at actA[e * (BM + 4) + r]), segment-wide L2 normalisation, optional copies to HBM.
+template <int THREADS, int BM, class Sync>
+__device__ __forceinline__ void mlp_prologue(const MlpParams &P, int64_t B, float *actA, int64_t b0, int tid, Sync sync,
+                                             bool write_hbm = true, int pad_to = 0) {
+  constexpr int ALD = BM + 4;
+  const pcv_mlp_desc &d = P.d;
+
+    constexpr int TPR = THREADS / BM;  // threads per row
+    const int row = tid / TPR, sub = tid % TPR;
+    const int64_t b = b0 + row;
+    float *x = actA + row;                 // element e at x[e * ALD]
+    if (b < B) {
+      for (int s = 0; s < d.n_segments; ++s) {
+        const pcv_segment &sg = d.seg[s];
+        float *xs = x + P.seg_off[s] * ALD;
+        if (sg.kind == PCV_SEG_DENSE) {
+          const float *src = (const float *)sg.ptr + b * sg.width;
+          for (int e = sub; e < sg.width; e += TPR) xs[e * ALD] = src[e];
+        } else if (sg.kind == PCV_SEG_ONEHOT) {
+          const float *r = (const float *)sg.ptr + b * sg.count;
+          float sum = 0.f;
+          for (int l = 0; l < sg.count; ++l) sum += r[l];
+          const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
+          for (int e = sub; e <= sg.count; e += TPR) xs[e * ALD] = (e == hot) ? 1.f : 0.f;
+        } else {  // GATHER
+          const float *tab = (const float *)sg.ptr;
+          const int n = sg.count * sg.width;
+          for (int e = sub; e < n; e += TPR) {
+            const int c = e / sg.width, k = e - c * sg.width;
+            xs[e * ALD] = tab[sg.idx[b * sg.count + c] * (int64_t)sg.width + k];
+          }
+        }
+      }
+    } else {
+      for (int e = sub; e < P.n_in0; e += TPR) x[e * ALD] = 0.f;
+    }
+    for (int e = P.n_in0 + sub; e < pad_to; e += TPR) x[e * ALD] = 0.f;   // k padding of the first layer (cluster engine)
+    sync();
+    // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order
+    for (int s = 0; s < d.n_segments; ++s) {
+      if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
+      const int w = P.seg_off[s + 1] - P.seg_off[s];
+      float *xs = x + P.seg_off[s] * ALD;
+      float ss = 0.f;
+      for (int e = 0; e < w; ++e) ss = fmaf(xs[e * ALD], xs[e * ALD], ss);  // every thread of the row: same value
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      sync();
+      for (int e = sub; e < w; e += TPR) xs[e * ALD] = xs[e * ALD] / nrm;
+      sync();
+    }
+    if (b < B && write_hbm) {
+      if (d.x0) {
+        float *dst = d.x0 + b * P.n_in0;
+        for (int e = sub; e < P.n_in0; e += TPR) dst[e] = x[e * ALD];
+      }
+      if (d.copy_seg >= 0) {
+        const int w = P.seg_off[d.copy_seg + 1] - P.seg_off[d.copy_seg];
+        const float *xs = x + P.seg_off[d.copy_seg] * ALD;
+        float *dst = d.out + b * d.out_ld;
+        for (int e = sub; e < w; e += TPR) dst[e] = xs[e * ALD];
+      }
+    }
+  }
+
+// Reparameterisation epilogue (cvae.py:79-83): z = eps * exp(0.5 * logvar) + mu from the last layer's
+// [mu | logvar] still in shared memory.
+template <int THREADS, int BM>
+__device__ __forceinline__ void mlp_reparam(const pcv_mlp_desc &d, const float *cur, int64_t b0, int64_t B, int tid) {
+  constexpr int ALD = BM + 4;
+  const int Z = d.latent;
+  const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
+  for (int e = tid; e < BM * Z; e += THREADS) {
+    const int row = e / Z, j = e - row * Z;
+    const int64_t b = b0 + row;
+    if (b >= B) continue;
+    const float mu = cur[j * ALD + row];
+    const float lv = cur[(Z + j) * ALD + row];
+    float eps;
+    if (d.eps) {
+      eps = d.eps[b * Z + j];
+    } else {
+      float n4[4];
+      normal4(d.seed, rng_off, b, j >> 2, n4);
+      eps = n4[j & 3];
+    }
+    const float sd = pcv_expf(lv * 0.5f);
+    d.z[b * Z + j] = eps * sd + mu;
+    if (d.eps_out) d.eps_out[b * Z + j] = eps;
+  }
 }
 
 // Thread mapping: THREADS = (256/CT column groups) x (row groups of RT rows); a thread owns
@@ -147,63 +240,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
       asm volatile("prefetch.global.L2 [%0];" ::"l"(wb + o));
   }
 
-  // ---------------- prologue: assemble x0 into actA (transposed) ----------------
-  {
-    constexpr int TPR = THREADS / BM;  // threads per row
-    const int row = tid / TPR, sub = tid % TPR;
-    const int64_t b = b0 + row;
-    float *x = actA + row;                 // element e at x[e * ALD]
-    if (b < B) {
-      for (int s = 0; s < d.n_segments; ++s) {
-        const pcv_segment &sg = d.seg[s];
-        float *xs = x + P.seg_off[s] * ALD;
-        if (sg.kind == PCV_SEG_DENSE) {
-          const float *src = (const float *)sg.ptr + b * sg.width;
-          for (int e = sub; e < sg.width; e += TPR) xs[e * ALD] = src[e];
-        } else if (sg.kind == PCV_SEG_ONEHOT) {
-          const float *r = (const float *)sg.ptr + b * sg.count;
-          float sum = 0.f;
-          for (int l = 0; l < sg.count; ++l) sum += r[l];
-          const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
-          for (int e = sub; e <= sg.count; e += TPR) xs[e * ALD] = (e == hot) ? 1.f : 0.f;
-        } else {  // GATHER
-          const float *tab = (const float *)sg.ptr;
-          const int n = sg.count * sg.width;
-          for (int e = sub; e < n; e += TPR) {
-            const int c = e / sg.width, k = e - c * sg.width;
-            xs[e * ALD] = tab[sg.idx[b * sg.count + c] * (int64_t)sg.width + k];
-          }
-        }
-      }
-    } else {
-      for (int e = sub; e < P.n_in0; e += TPR) x[e * ALD] = 0.f;
-    }
-    __syncthreads();
-    // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order
-    for (int s = 0; s < d.n_segments; ++s) {
-      if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
-      const int w = P.seg_off[s + 1] - P.seg_off[s];
-      float *xs = x + P.seg_off[s] * ALD;
-      float ss = 0.f;
-      for (int e = 0; e < w; ++e) ss = fmaf(xs[e * ALD], xs[e * ALD], ss);  // every thread of the row: same value
-      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-      __syncthreads();
-      for (int e = sub; e < w; e += TPR) xs[e * ALD] = xs[e * ALD] / nrm;
-      __syncthreads();
-    }
-    if (b < B) {
-      if (d.x0) {
-        float *dst = d.x0 + b * P.n_in0;
-        for (int e = sub; e < P.n_in0; e += TPR) dst[e] = x[e * ALD];
-      }
-      if (d.copy_seg >= 0) {
-        const int w = P.seg_off[d.copy_seg + 1] - P.seg_off[d.copy_seg];
-        const float *xs = x + P.seg_off[d.copy_seg] * ALD;
-        float *dst = d.out + b * d.out_ld;
-        for (int e = sub; e < w; e += TPR) dst[e] = xs[e * ALD];
-      }
-    }
-  }
+  mlp_prologue<THREADS, BM>(P, B, actA, b0, tid, [] { __syncthreads(); });
 
   // ---------------- layers ----------------
   float *cur = actA, *nxt = actB;
@@ -305,29 +342,7 @@ __device__ __forceinline__ void mlp_block(const MlpParams &P, int64_t B, float *
   }
   __syncthreads();
 
-  // ---------------- reparameterisation epilogue ----------------
-  if (d.latent > 0) {
-    const int Z = d.latent;
-    const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
-    for (int e = tid; e < BM * Z; e += THREADS) {
-      const int row = e / Z, j = e - row * Z;
-      const int64_t b = b0 + row;
-      if (b >= B) continue;
-      const float mu = cur[j * ALD + row];
-      const float lv = cur[(Z + j) * ALD + row];
-      float eps;
-      if (d.eps) {
-        eps = d.eps[b * Z + j];
-      } else {
-        float n4[4];
-        normal4(d.seed, rng_off, b, j >> 2, n4);
-        eps = n4[j & 3];
-      }
-      const float sd = pcv_expf(lv * 0.5f);
-      d.z[b * Z + j] = eps * sd + mu;
-      if (d.eps_out) d.eps_out[b * Z + j] = eps;
-    }
-  }
+  if (d.latent > 0) mlp_reparam<THREADS, BM>(d, cur, b0, B, tid);
 }
 
 template <int CT, int RT, int THREADS>
@@ -351,6 +366,324 @@ mlp_fwd2_kernel(const MlpParams2 P, int64_t B) {
   __threadfence_block();
   __syncthreads();
   mlp_block<CT, RT, THREADS>(P.b, B, smem);
+}
+
+// ===========================================================================
+// Packed-weight cluster engine (inference).  The streaming engine above makes every CTA pull the
+// whole weight set of the block through L2 (128 CTAs x 360 KB at B=1024): measured L2-bound.
+// Here a CLUSTER of 4 CTAs owns 32 batch rows and splits every layer's output columns in 64-wide
+// blocks (block j -> CTA j mod 4), so each CTA streams a quarter of the weights:
+//   * weights are pre-tiled once by pcv_mlp_pack into the shared-memory image a k-chunk needs:
+//     tile (block j, chunk kc) = [32][nbw] floats, element (kk, n) = W[64 j + n][kc + kk] (zero
+//     padded), nbw = min(64, round_up32(n_out - 64 j)) -> a chunk is ONE TMA bulk copy issued by a
+//     producer warp into an 8-stage mbarrier ring (no per-chunk __syncthreads, no weight LDG/STS);
+//   * 8 compute warps, warp = 4 rows, lane = 2 columns (a single warp per scheduler issues an FFMA
+//     only every other cycle: measured, so two warps share each scheduler);
+//   * a block's outputs are written straight into the next layer's activation buffer of ALL four
+//     CTAs (st.shared::cluster) and one cluster barrier per layer publishes them;
+//   * narrow layers (<= 96 outputs: heads, last layers) split the ROWS over the cluster instead
+//     (rank r = rows 8r..8r+7, warp = row, lane = column), every rank streaming the small tiles.
+// Same arithmetic contract (sequential-k FMA chain) -> bit-identical to the streaming engine.
+// ===========================================================================
+#ifdef PCV_TC_TRACE
+__device__ long long g_mlp_trace[4][32];   // [cluster rank of cluster 0][event]
+#define MLP_TRACE(i) do { if (blockIdx.x < 4 && threadIdx.x == 0) g_mlp_trace[blockIdx.x][i] = clock64(); } while (0)
+#else
+#define MLP_TRACE(i) do { } while (0)
+#endif
+
+constexpr int MLPC_CL = 4;                 // CTAs per cluster
+constexpr int MLPC_BN = 64;                // output columns per block
+constexpr int MLPC_BM = 32;                // batch rows per cluster
+constexpr int MLPC_ALD = MLPC_BM + 4;      // activation row stride (floats)
+constexpr int MLPC_STAGES = 8;
+constexpr int MLPC_TILE_FLOATS = MLP_KC * MLPC_BN;   // 8 KB
+constexpr int MLPC_ROWSPLIT_MAX = 96;      // layers up to this wide split the rows, not the columns, over the cluster
+constexpr int MLPC_NC = 256;               // compute threads: 8 warps = 8 row groups of 4 rows
+
+__host__ __device__ __forceinline__ int mlpc_nbw(int n_out, int nb) {
+  const int w = ((n_out - nb) + 31) & ~31;
+  return w < MLPC_BN ? w : MLPC_BN;
+}
+__host__ __device__ __forceinline__ int64_t mlpc_packed_floats(int n_in, int n_out) {
+  const int64_t kpad = (n_in + MLP_KC - 1) / MLP_KC * MLP_KC;
+  int64_t cols = 0;
+  for (int nb = 0; nb < n_out; nb += MLPC_BN) cols += mlpc_nbw(n_out, nb);
+  return kpad * cols;
+}
+
+__global__ void mlp_pack_kernel(const float *__restrict__ W, int K, int NO, float *__restrict__ Wp, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t kpad = (K + MLP_KC - 1) / MLP_KC * MLP_KC;
+  const int j = (int)(e / (kpad * MLPC_BN));           // every block before the last is 64 wide
+  const int nb = j * MLPC_BN;
+  const int nbw = mlpc_nbw(NO, nb);
+  const int64_t local = e - (int64_t)j * kpad * MLPC_BN;
+  const int k = (int)(local / nbw), n = (int)(local % nbw);   // tile kc = k / 32 at kc * 32 * nbw, row kk = k % 32
+  Wp[e] = (nb + n < NO && k < K) ? W[(int64_t)(nb + n) * K + k] : 0.f;
+}
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t local_addr, uint32_t rank, float4 v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void st_cluster_f1(uint32_t local_addr, uint32_t rank, float v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float *actA, float *actB, const float *stage,
+                                           unsigned long long *full, unsigned long long *empty, uint32_t &g,
+                                           uint32_t crank) {
+  constexpr int CT = 2, RT = 4;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;   // warp = row group (4 rows), lane = 2 columns
+  const int64_t b0 = (int64_t)(blockIdx.x / MLPC_CL) * MLPC_BM;
+  const pcv_mlp_desc &d = P.d;
+  auto csync = [] { asm volatile("bar.sync 1, %0;" ::"n"(MLPC_NC) : "memory"); };
+
+  // every CTA of the cluster assembles the (same) input rows in its own buffer; rank 0 writes the HBM copies
+  MLP_TRACE(1);
+  // every k range is padded to a multiple of 32 with zeros (activation rows here and in the epilogues
+  // below, weight tiles by pcv_mlp_pack): adding a*0 to a sequential FMA chain never changes it
+  mlp_prologue<MLPC_NC, MLPC_BM>(P, B, actA, b0, tid, csync, crank == 0, (P.n_in0 + MLP_KC - 1) / MLP_KC * MLP_KC);
+  MLP_TRACE(2);
+
+  float *cur = actA, *nxt = actB;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const pcv_linear L = d.layer[l];
+    const bool last = (l == d.n_layers - 1);
+    const int K = L.n_in;
+    if (L.n_out > MLPC_ROWSPLIT_MAX) {
+      // ---- wide layer: column split, 64-wide block j -> rank j mod 4; warp = 4 rows, lane = 2 columns
+      for (int nb = (int)crank * MLPC_BN; nb < L.n_out; nb += MLPC_CL * MLPC_BN) {
+        const int nbw = mlpc_nbw(L.n_out, nb);
+        const bool active = lane * CT < nbw;   // lanes past the (padded) block only keep the ring moving
+        float acc[RT][CT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
+        for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
+          const int s = g % MLPC_STAGES;
+          mbar_wait(&full[s], (g / MLPC_STAGES) & 1);
+          if (active) {
+            const float *ws = stage + (size_t)s * MLPC_TILE_FLOATS + lane * CT;
+            const float *ap = cur + (size_t)kc * MLPC_ALD + wrp * RT;
+            auto load_ops = [&](int kk, float (&a)[RT], float (&w)[CT]) {
+              const float4 a0 = *reinterpret_cast<const float4 *>(ap + kk * MLPC_ALD);
+              a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+              const float2 w2 = *reinterpret_cast<const float2 *>(ws + kk * nbw);
+              w[0] = w2.x; w[1] = w2.y;
+            };
+            auto fma_ops = [&](const float (&a)[RT], const float (&w)[CT]) {
+#pragma unroll
+              for (int r = 0; r < RT; ++r)
+#pragma unroll
+                for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
+            };
+            // two warps per scheduler: the operands of the next three k-steps are in flight while
+            // this step's 8 FMAs issue
+            float a0[RT], a1[RT], a2[RT], a3[RT], w0[CT], w1[CT], w2[CT], w3[CT];
+            load_ops(0, a0, w0);
+            load_ops(1, a1, w1);
+            load_ops(2, a2, w2);
+#pragma unroll
+            for (int kk = 0; kk < MLP_KC; kk += 4) {
+              load_ops(kk + 3, a3, w3);
+              fma_ops(a0, w0);
+              if (kk + 4 < MLP_KC) load_ops(kk + 4, a0, w0);
+              fma_ops(a1, w1);
+              if (kk + 5 < MLP_KC) load_ops(kk + 5, a1, w1);
+              fma_ops(a2, w2);
+              if (kk + 6 < MLP_KC) load_ops(kk + 6, a2, w2);
+              fma_ops(a3, w3);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done reading the stage
+        }
+        // bias + activation -> the next layer's buffer of all four CTAs (+ HBM); padded columns -> 0
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const int n = nb + lane * CT + c;
+          if (n < nb + nbw) {
+            const bool real = n < L.n_out;
+            const float bias = real ? __ldg(L.b + n) : 0.f;
+            float v[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) v[r] = real ? apply_act(acc[r][c] + bias, L.act) : 0.f;
+            const uint32_t np = smem_u32(nxt + (size_t)n * MLPC_ALD + wrp * RT);
+#pragma unroll
+            for (uint32_t t = 0; t < MLPC_CL; ++t) st_cluster_f4(np, t, make_float4(v[0], v[1], v[2], v[3]));
+            if (real) {
+#pragma unroll
+              for (int r = 0; r < RT; ++r) {
+                const int64_t b = b0 + wrp * RT + r;
+                if (b < B) {
+                  if (last) d.out[b * d.out_ld + d.out_col0 + n] = v[r];
+                  else if (d.acts[l]) d.acts[l][b * L.n_out + n] = v[r];
+                }
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // ---- narrow layer: a column split would idle three CTAs (and most lanes), so the ROWS are split:
+      // rank r computes rows 8r..8r+7 for every column; warp = one row, lane = columns lane (+32)
+      const int row = (int)crank * (MLPC_BM / MLPC_CL) + wrp;
+      for (int nb = 0; nb < L.n_out; nb += MLPC_BN) {
+        const int nbw = mlpc_nbw(L.n_out, nb);
+        const bool two = nbw > 32;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
+          const int s = g % MLPC_STAGES;
+          mbar_wait(&full[s], (g / MLPC_STAGES) & 1);
+          const float *ws = stage + (size_t)s * MLPC_TILE_FLOATS + lane;
+          const float *ap = cur + (size_t)kc * MLPC_ALD + row;
+          if (two) {
+#pragma unroll
+            for (int kk = 0; kk < MLP_KC; ++kk) {
+              const float a = ap[kk * MLPC_ALD];
+              acc0 = fmaf(a, ws[kk * 64], acc0);
+              acc1 = fmaf(a, ws[kk * 64 + 32], acc1);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < MLP_KC; ++kk) acc0 = fmaf(ap[kk * MLPC_ALD], ws[kk * 32], acc0);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int n = nb + lane + 32 * c;
+          if (n < nb + nbw) {
+            const bool real = n < L.n_out;
+            const float v = real ? apply_act((c ? acc1 : acc0) + __ldg(L.b + n), L.act) : 0.f;
+            const uint32_t np = smem_u32(nxt + (size_t)n * MLPC_ALD + row);
+#pragma unroll
+            for (uint32_t t = 0; t < MLPC_CL; ++t) st_cluster_f1(np, t, v);
+            const int64_t b = b0 + row;
+            if (real && b < B) {
+              if (last) d.out[b * d.out_ld + d.out_col0 + n] = v;
+              else if (d.acts[l]) d.acts[l][b * L.n_out + n] = v;
+            }
+          }
+        }
+      }
+    }
+    MLP_TRACE(3 + 2 * l);
+    cluster_sync_all();   // every CTA's part of nxt has landed everywhere; cur is no longer read anywhere
+    MLP_TRACE(4 + 2 * l);
+    float *t = cur; cur = nxt; nxt = t;
+  }
+  if (d.latent > 0 && crank == 0) mlp_reparam<MLPC_NC, MLPC_BM>(d, cur, b0, B, tid);
+}
+
+// warps 0-7 compute; warp 8 streams this CTA's weight tiles of the whole launch (both blocks of a
+// chain back to back: the second block's weights prefetch while the first one finishes)
+__global__ void __cluster_dims__(MLPC_CL, 1, 1) __launch_bounds__(MLPC_NC + 32)
+mlp_cluster_kernel(const MlpParams2 P, int n_blocks, int64_t B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *stage = reinterpret_cast<float *>(smem_raw);                               // [8][32][64]
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(stage + MLPC_STAGES * MLPC_TILE_FLOATS);
+  unsigned long long *empty = full + MLPC_STAGES;
+  float *actA = reinterpret_cast<float *>(empty + MLPC_STAGES);                      // 16-byte aligned
+  float *actB = actA + (size_t)P.a.ld * MLPC_ALD;
+  const uint32_t crank = cluster_rank();
+  MLP_TRACE(0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MLPC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MLPC_NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();   // nobody writes into a peer's shared memory before that peer is running
+  if (threadIdx.x >= MLPC_NC) {
+    // The cluster barriers count every thread of the cluster, so this warp takes part in each of
+    // them, in the compute threads' order (one per layer, one between chained blocks).  It must
+    // never BLOCK on a barrier before the tiles the compute threads need to reach it are issued:
+    // arrive(e) follows the issue of layer e's tiles, and the matching wait is deferred until
+    // the next layer's tiles are issued too (so the producer runs up to one layer ahead).
+    // cold start (weights not in L2, e.g. the first call after other work evicted them): request this
+    // rank's tiles of the whole launch into L2 up front, clusters taking turns over the tile list
+    {
+      const int lane = threadIdx.x & 31;
+      const unsigned ncl = gridDim.x / MLPC_CL, cl = blockIdx.x / MLPC_CL;
+      unsigned t = 0;
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const pcv_mlp_desc &d = blk ? P.b.d : P.a.d;
+        for (int l = 0; l < d.n_layers; ++l) {
+          const int K = d.layer[l].n_in, NO = d.layer[l].n_out;
+          const int64_t kpad = (K + MLP_KC - 1) / MLP_KC * MLP_KC;
+          const bool rowsplit = NO <= MLPC_ROWSPLIT_MAX;
+          for (int nb = rowsplit ? 0 : (int)crank * MLPC_BN; nb < NO; nb += (rowsplit ? 1 : MLPC_CL) * MLPC_BN, ++t) {
+            if (t % 8 != cl % 8 && ncl >= 8) continue;
+            const char *src = reinterpret_cast<const char *>(d.layer[l].Wp + (int64_t)nb * kpad);
+            const int64_t bytes = kpad * mlpc_nbw(NO, nb) * (int64_t)sizeof(float);
+            for (int64_t o = (int64_t)lane * 128; o < bytes; o += 32 * 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+          }
+        }
+      }
+    }
+    uint32_t g = 0;
+    bool pending = false;
+    auto event = [&]() {
+      __syncwarp();
+      if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      pending = true;
+    };
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const pcv_mlp_desc &d = blk ? P.b.d : P.a.d;
+      if (blk) event();   // the barrier between chained blocks
+      for (int l = 0; l < d.n_layers; ++l) {
+        if (threadIdx.x == MLPC_NC) {
+          const int K = d.layer[l].n_in, NO = d.layer[l].n_out;
+          const int64_t kpad = (K + MLP_KC - 1) / MLP_KC * MLP_KC;
+          const bool rowsplit = NO <= MLPC_ROWSPLIT_MAX;   // every rank needs every block of a narrow layer
+          for (int nb = rowsplit ? 0 : (int)crank * MLPC_BN; nb < NO; nb += (rowsplit ? 1 : MLPC_CL) * MLPC_BN) {
+            const int nbw = mlpc_nbw(NO, nb);
+            const float *src = d.layer[l].Wp + (int64_t)nb * kpad;
+            const uint32_t bytes = (uint32_t)(MLP_KC * nbw * sizeof(float));
+            for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
+              const int s = g % MLPC_STAGES;
+              mbar_wait(&empty[s], ((g / MLPC_STAGES) & 1) ^ 1);
+              mbar_expect_tx(&full[s], bytes);
+              tma_bulk_load(stage + (size_t)s * MLPC_TILE_FLOATS, src + (int64_t)kc * nbw, bytes, &full[s]);
+            }
+          }
+        }
+        event();   // the barrier that ends layer l
+      }
+    }
+    if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    return;
+  }
+  uint32_t g = 0;
+  mlpc_block(P.a, B, actA, actB, stage, full, empty, g, crank);
+  MLP_TRACE(20);
+  if (n_blocks > 1) {
+    // block B's prologue reads what rank 0 just wrote to HBM for the cluster's batch rows (z)
+    __threadfence();
+    cluster_sync_all();
+    mlpc_block(P.b, B, actA, actB, stage, full, empty, g, crank);
+  }
 }
 
 // KL(q||p) summed (train_generative.py:61) with analytic gradients; one CTA,
@@ -443,11 +776,42 @@ static int mlp_prepare(const pcv_mlp_desc *d, MlpParams *Pp, int *maxw_out, int 
   return PCV_OK;
 }
 
+static bool mlp_all_packed(const MlpParams *P) {
+  for (int l = 0; l < P->d.n_layers; ++l)
+    if (P->d.layer[l].Wp == nullptr) return false;
+  return true;
+}
+
+// packed-weight cluster engine: 32 rows per cluster of 4 CTAs
+static int mlp_launch_cluster(const MlpParams *Pa, const MlpParams *Pb, int64_t B, int ld, cudaStream_t st, bool *done) {
+  *done = false;
+  ld = (ld + MLP_KC - 1) / MLP_KC * MLP_KC;   // k ranges / column blocks are zero-padded to multiples of 32
+  const size_t smem = (size_t)MLPC_STAGES * MLPC_TILE_FLOATS * sizeof(float) + 2 * MLPC_STAGES * 8 +
+                      (size_t)2 * ld * MLPC_ALD * sizeof(float);
+  if (smem > 227 * 1024) return PCV_OK;   // does not fit: the caller falls back to the streaming engine
+  const int64_t clusters = (B + MLPC_BM - 1) / MLPC_BM;
+  MlpParams2 P2;
+  P2.a = *Pa;
+  P2.b = Pb ? *Pb : *Pa;
+  P2.a.ld = ld; P2.b.ld = ld;
+  PCV_CUDA(cudaFuncSetAttribute(mlp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mlp_cluster_kernel<<<(unsigned)(clusters * MLPC_CL), MLPC_NC + 32, smem, st>>>(P2, Pb ? 2 : 1, B);
+  PCV_LAUNCH_CHECK();
+  *done = true;
+  return PCV_OK;
+}
+
 static int mlp_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaStream_t st) {
   int sm_count = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (mlp_all_packed(Pa) && (!Pb || mlp_all_packed(Pb))) {
+    const int ldp = Pb ? (Pa->ld > Pb->ld ? Pa->ld : Pb->ld) : Pa->ld;
+    bool done = false;
+    int rc = mlp_launch_cluster(Pa, Pb, B, ldp, st, &done);
+    if (rc != PCV_OK || done) return rc;
+  }
   // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs (and use 16 warps per CTA)
   const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
   const int BM = 8 * CT;
@@ -497,6 +861,29 @@ int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_st
   Pb.ld = (wb + 3) & ~3;
   return mlp_launch(&Pa, &Pb, B, (cudaStream_t)stream);
 }
+
+size_t pcv_mlp_packed_bytes(int n_in, int n_out) {
+  if (n_in <= 0 || n_out <= 0) return 0;
+  return (size_t)mlpc_packed_floats(n_in, n_out) * sizeof(float);
+}
+
+int pcv_mlp_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream) {
+  PCV_CHECK_ARG(W && packed, "NULL pointer");
+  PCV_CHECK_ARG(n_in > 0 && n_out > 0 && n_in <= PCV_MAX_WIDTH && n_out <= PCV_MAX_WIDTH, "bad layer shape");
+  PCV_CHECK_ARG(((uintptr_t)packed & 127) == 0, "packed buffer must be 128-byte aligned");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  const int64_t total = mlpc_packed_floats(n_in, n_out);
+  mlp_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, n_in, n_out, packed, total);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+#ifdef PCV_TC_TRACE
+int pcv_debug_mlp_trace(long long *host4x32) {
+  return (int)cudaMemcpyFromSymbol(host4x32, g_mlp_trace, sizeof(long long) * 4 * 32);
+}
+#endif
 
 int pcv_kl_fwd_bwd(const float *mu, const float *logvar, const float *pmu, const float *plogvar,
                    int64_t n, float *kl_out, float *dmu, float *dlogvar, float *dpmu,

@@ -4,6 +4,10 @@ GraphedSlateGenerator captures `model.recommend(ctx, users, return_item=True)` f
 response model's score of the generated slates into ONE CUDA graph over static buffers.  Random
 draws stay fresh on every replay: the Philox row counter lives in device memory
 (pcv_*.offset_dev) and the last node of the graph advances it (pcv_counter_add).
+
+The graph reads the MLP weights through the pre-tiled copies of the packed engine (ops.packed_weight)
+and the concatenated latent heads, i.e. it SNAPSHOTS the weights at capture time: build a new
+generator after the model has been trained further.
 """
 import torch
 

@@ -4,6 +4,7 @@ torch is plumbing here (device memory, streams, autograd bookkeeping); all the
 arithmetic of the hot path happens in libpcv_b200.so.  Every function raises if
 handed a non-CUDA tensor — there is no fallback.
 """
+import collections
 import ctypes
 
 import torch
@@ -248,6 +249,51 @@ class Gather:
         keep.extend([self.table, self.idx])
 
 
+# ---- packed weights of the TMA MLP engine (inference): one pre-tiled copy per weight tensor, rebuilt
+# IN PLACE when the tensor's version counter moves (so CUDA graphs that captured the pointer stay valid
+# after `repack_stale()`).  An entry pins the weight's storage, so a data_ptr can not be recycled by
+# another tensor while it is cached.
+_PACKED = collections.OrderedDict()   # data_ptr -> [version, shape, storage, packed, weight]
+_PACKED_MAX = 512
+
+
+def _pack_into(W, packed):
+    with torch.cuda.device(W.device):
+        L.check(L.load().pcv_mlp_pack(_ptr(W), W.shape[1], W.shape[0], _ptr(packed), _stream()), "pcv_mlp_pack")
+
+
+def packed_weight(W):
+    """Pre-tiled copy of an nn.Linear weight for pcv_linear.Wp (cached per tensor + version)."""
+    key = W.data_ptr()
+    hit = _PACKED.get(key)
+    if hit is not None and hit[1] == tuple(W.shape):
+        if hit[0] != W._version:
+            _pack_into(W, hit[3])
+            hit[0] = W._version
+        _PACKED.move_to_end(key)
+        return hit[3]
+    nbytes = L.load().pcv_mlp_packed_bytes(W.shape[1], W.shape[0])
+    packed = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+    _pack_into(W, packed)
+    if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not outlive its graph in the cache
+        _PACKED[key] = [W._version, tuple(W.shape), W.untyped_storage(), packed, W]
+        while len(_PACKED) > _PACKED_MAX:
+            _PACKED.popitem(last=False)
+    return packed
+
+
+def repack_stale():
+    """Re-tile (in place) every cached weight whose tensor changed since it was packed; call it after
+    updating weights that a captured CUDA graph reads through the packed copies."""
+    for hit in _PACKED.values():
+        if hit[0] != hit[4]._version:
+            _pack_into(hit[4], hit[3])
+            hit[0] = hit[4]._version
+
+
+PACK_WEIGHTS = True   # False: always stream nn.Linear weights as they are (the training engine)
+
+
 def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
               latent=0, eps=None, seed=0, offset=0, offset_dev=None):
     """Build a pcv_mlp_desc (+ its output tensors); returns (desc, results, keep-alive list, device)."""
@@ -268,6 +314,10 @@ def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_se
         d.layer[i].W, d.layer[i].b = W.data_ptr(), b.data_ptr()
         d.layer[i].n_in, d.layer[i].n_out, d.layer[i].act = W.shape[1], W.shape[0], act
         keep.extend([W, b])
+        if not save and PACK_WEIGHTS:
+            Wp = packed_weight(W)
+            d.layer[i].Wp = Wp.data_ptr()
+            keep.append(Wp)
         prev = W.shape[0]
     n_out = prev
     if out is None:

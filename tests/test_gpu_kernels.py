@@ -170,6 +170,52 @@ def test_mlp_block_bitexact(ops, B, dims):
         assert np.array_equal(N(a), h)
 
 
+@pytest.mark.parametrize("B", [1, 15, 64, 1000, 1300, 5000])
+@pytest.mark.parametrize("dims", [(54, 256, 256, 32), (38, 64, 8), (47, 300, 512, 40), (33, 16), (62, 256, 72)])
+def test_mlp_packed_engine_bitexact(ops, B, dims):
+    """Inference (save=False) runs the packed-weight TMA engine: bit-identical to the oracle and to the
+    streaming engine, also after the weights change in place (cache re-pack on the version counter)."""
+    rng = np.random.default_rng(B + sum(dims))
+    acts = [1] * (len(dims) - 2) + [0]
+    segs, layers, x, ref = _mlp_case(ops, rng, B, dims, acts, 3)
+    got = ops.mlp_forward(segs, layers, B)
+    assert np.array_equal(N(got["out"]), ref)
+    ops.PACK_WEIGHTS = False
+    try:
+        plain = ops.mlp_forward(segs, layers, B)
+    finally:
+        ops.PACK_WEIGHTS = True
+    assert torch.equal(got["out"], plain["out"])
+    layers[0][0].mul_(0.5)                          # in-place update -> version bump -> re-pack
+    h = x
+    for i, (W, b, a) in enumerate(layers):
+        h = oracle.linear(h, N(W), N(b), a)
+    assert np.array_equal(N(ops.mlp_forward(segs, layers, B)["out"]), h)
+
+
+def test_mlp_packed_chain_and_reparam(ops):
+    """Two chained blocks (prior -> z -> next block) on the packed engine == two separate launches."""
+    rng = np.random.default_rng(5)
+    B, Z = 777, 16
+    r = (rng.random((B, 5)) < 0.5).astype(np.float32)
+    eps = rng.standard_normal((B, Z)).astype(np.float32)
+    mk = lambda o, i: (T((rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32)), T(rng.standard_normal(o).astype(np.float32) * 0.1))
+    pl = [mk(128, 6) + (1,), mk(128, 128) + (1,), mk(2 * Z, 128) + (0,)]
+    nl = [mk(256, Z + 6) + (1,), mk(256, 256) + (1,), mk(8, 256) + (0,)]
+    cond = ops.OneHot(T(r))
+    first = ([cond], pl, dict(latent=Z, eps=T(eps)))
+    ra, rb = ops.mlp_forward_chain(first, lambda res: ([ops.Dense(res["z"]), cond], nl, {}), B)
+    h = oracle.condition(r)
+    for (W, b, a) in pl:
+        h = oracle.linear(h, N(W), N(b), a)
+    z = oracle.reparam(h[:, :Z], h[:, Z:], eps)
+    assert np.array_equal(N(ra["out"]), h) and np.array_equal(N(ra["z"]), z)
+    g = np.concatenate([z, oracle.condition(r)], 1)
+    for (W, b, a) in nl:
+        g = oracle.linear(g, N(W), N(b), a)
+    assert np.array_equal(N(rb["out"]), g)
+
+
 def test_mlp_reparam_and_relu(ops):
     rng = np.random.default_rng(0)
     B, Z = 100, 16
