@@ -381,7 +381,7 @@ mlp_fwd2_kernel(const MlpParams2 P, int64_t B) {
 //     only every other cycle: measured, so two warps share each scheduler);
 //   * a block's outputs are written straight into the next layer's activation buffer of ALL four
 //     CTAs (st.shared::cluster) and one cluster barrier per layer publishes them;
-//   * narrow layers (<= 96 outputs: heads, last layers) split the ROWS over the cluster instead
+//   * narrow layers (<= 64 outputs: heads, last layers) split the ROWS over the cluster instead
 //     (rank r = rows 8r..8r+7, warp = row, lane = column), every rank streaming the small tiles.
 // Same arithmetic contract (sequential-k FMA chain) -> bit-identical to the streaming engine.
 // ===========================================================================
@@ -398,7 +398,7 @@ constexpr int MLPC_BM = 32;                // batch rows per cluster
 constexpr int MLPC_ALD = MLPC_BM + 4;      // activation row stride (floats)
 constexpr int MLPC_STAGES = 8;
 constexpr int MLPC_TILE_FLOATS = MLP_KC * MLPC_BN;   // 8 KB
-constexpr int MLPC_ROWSPLIT_MAX = 96;      // layers up to this wide split the rows, not the columns, over the cluster
+constexpr int MLPC_ROWSPLIT_MAX = 64;      // layers up to this wide split the rows, not the columns, over the cluster
 constexpr int MLPC_NC = 256;               // compute threads: 8 warps = 8 row groups of 4 rows
 
 __host__ __device__ __forceinline__ int mlpc_nbw(int n_out, int nb) {

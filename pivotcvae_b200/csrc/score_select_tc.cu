@@ -53,7 +53,7 @@ constexpr int SEL_SW = TC_BN / SEL_SLICES;            // columns per slice
 constexpr int SEL_THREADS = 64 + 32 * SEL_EPI_WARPS;  // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
 constexpr int SEL_STAGES = 12;                        // 8 KB table tiles in flight
 constexpr int TC_CAP = 16;                            // in-kernel recorded-chunk list capacity per (slice, row)
-constexpr int TC_OUT = 8;                            // recorded chunks handed to the refine kernel per (stream, row)
+constexpr int TC_OUT = 4;                            // recorded chunks handed to the refine kernel per (stream, row)
 
 struct __align__(1024) TcSmem {
   float b[SEL_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
@@ -442,17 +442,18 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
       for (int e = 0; e < TC_OUT; ++e) ents[e] = out_ent[((int64_t)s * TC_OUT + e) * M + row];   // e >= cnt: stale, ignored
     }
   };
+  // issue every independent load before the first use: the first 32 streams' running maxima, their
+  // lists, the query row and the row's overflow winner all arrive in ONE memory round trip
   int cnt;
   unsigned long long ents[TC_OUT];
-  float R = -INFINITY;
-  for (int s = lane; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
+  float R = (lane < n_streams) ? out_r[(int64_t)lane * M + row] : -INFINITY;
   load_group(0, cnt, ents);
+  const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+  const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+  const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
+  for (int s = lane + 32; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
   float q[TC_D];
-  {
-    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-    q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
-  }
+  q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
   float ss = 0.f;
 #pragma unroll
   for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
@@ -505,7 +506,6 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
     if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
   }
   if (lane == 0) {
-    const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
     row_best[row] = 0ull;                          // leave the workspace zeroed for the next call
     if (row == 0) *ovf_count_reset = 0u;
     if (pb) {
