@@ -212,6 +212,11 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
     const int slice = (warp - 2) >> 2;        // which SEL_SW columns of every 256-column tile
     const int trow = quarter * 32 + lane;
     unsigned long long *list = &S.cand[slice][0][trow];  // entry e at list[e * TC_BM]
+    // loop invariants pinned in registers (an opaque mov keeps the compiler from re-deriving them per tile)
+    uint32_t tfull_u32, tempty_u32, taddr0;
+    asm volatile("mov.u32 %0, %1;" : "=r"(tfull_u32) : "r"(smem_u32(&S.tfull[0])));
+    asm volatile("mov.u32 %0, %1;" : "=r"(tempty_u32) : "r"(smem_u32(&S.tempty[0])));
+    asm volatile("mov.u32 %0, %1;" : "=r"(taddr0) : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slice * SEL_SW)));
     uint32_t gt = 0;
     float r = 0.f, thr = 0.f, band = 0.f;   // per-row state of the current segment
     for (int64_t u = u_begin; u < u_end;) {
@@ -278,29 +283,30 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       };
 
       constexpr int NCH = SEL_SW / 32;  // chunks per slice per tile (even)
-      for (int t = 0; t < n_tiles; ++t, ++gt) {
-        const int buf = gt & 1;
-        const uint32_t bph = (gt >> 1) & 1;
-        mbar_wait(&S.tfull[buf], bph);
+      // per-tile bookkeeping kept to 32-bit adds: shared addresses of the barriers, the first item of this
+      // slice in the tile, the number of tiles that need no tail mask
+      const int n_full = max(0, min(n_tiles, (int)(n_rows / TC_BN) - ct0));
+      const bool exch = live && n_tiles >= 8;
+      int32_t jb0 = (int32_t)j_begin + slice * SEL_SW;
+      for (int t = 0; t < n_tiles; ++t, ++gt, jb0 += TC_BN) {
+        const uint32_t buf = gt & 1;
+        mbar_wait_u32(tfull_u32 + buf * 8, (gt >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (threadIdx.x == 64 && gt < 8) TC_TRACE(5 + gt);
-        const int64_t tile_j0 = j_begin + (int64_t)t * TC_BN + slice * SEL_SW;
-        const int n_valid = (int)min((int64_t)SEL_SW, j_end - tile_j0);  // may be <= 0
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + slice * SEL_SW);
-        const int32_t jb0 = (int32_t)tile_j0;
+        const uint32_t taddr = taddr0 + buf * TC_BN;
         uint32_t va[32], vb[32];
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
         TC_LD32(va, taddr);
         // (first tiles of a long segment, while the TMEM load is in flight) exchange the running max with the
-        // other column slice.  The slices are never more than the two TMEM buffers apart, so with >= 8 tiles
-        // per exchanging segment a slice can not read a value the other one published for a LATER segment.
-        if (live && t < 4 && n_tiles >= 8) {
+        // other column slices.  The slices are never more than the two TMEM buffers apart, so with >= 8 tiles
+        // per exchanging segment a slice can not read a value another one published for a LATER segment.
+        if (exch && t < 4) {
           const float sh = S.rmax[trow];
           if (sh > r) { r = sh; thr = r - band; }
           else if (r > sh) S.rmax[trow] = r;
         }
         TC_WAIT_LD(va);
-        if (n_valid == SEL_SW) {
+        if (t < n_full) {
 #pragma unroll
           for (int c = 0; c < NCH; c += 2) {
             TC_LD32(vb, taddr + (c + 1) * 32);
@@ -310,7 +316,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
             process(vb, jb0 + (c + 1) * 32);
             if (c + 2 < NCH) TC_WAIT_LD(va);
           }
-        } else {  // last tile of the range: mask the columns beyond j_end
+        } else {  // last tile of the table: mask the columns beyond its end
+          const int n_valid = (int)min((int64_t)SEL_SW, j_end - (int64_t)jb0);  // may be <= 0
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
             if (c > 0) { TC_LD32(va, taddr + c * 32); TC_WAIT_LD(va); }
@@ -320,7 +327,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.tempty[buf]);
+        if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
       }
       if (live) {
         // hand the surviving chunks of this (slot, slice) stream to the refine kernel

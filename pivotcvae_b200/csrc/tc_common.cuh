@@ -39,6 +39,22 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
       "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
+// same, on a precomputed 32-bit shared address (keeps the generic->shared conversion out of hot loops)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
 // TMA bulk copy global -> shared (contiguous bytes), completion on an mbarrier
 __device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, uint32_t bytes, void *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
