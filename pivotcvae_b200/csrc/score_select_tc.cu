@@ -36,6 +36,7 @@ namespace pcv {
 // Optional phase trace of CTA 0 (profiles/trace_select.py builds a separate library with -DPCV_TC_TRACE).
 #ifdef PCV_TC_TRACE
 __device__ long long g_tc_trace[16];
+__device__ long long g_tc_mma[16];   // MMA issuer, tiles 40..43: tempty passed / operands ready (just before the issue)
 __device__ long long g_tc_cta[4][256];   // per CTA: clock64 at entry / exit, globaltimer at entry / exit
 __device__ __forceinline__ long long tc_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_TRACE(i) do { if (blockIdx.x == 0) g_tc_trace[i] = clock64();                                          \
@@ -196,8 +197,14 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
           const int buf = gt & 1;
           const uint32_t bph = (gt >> 1) & 1;
           mbar_wait(&S.tempty[buf], bph ^ 1);
+#ifdef PCV_TC_TRACE
+          if (blockIdx.x == 0 && gt >= 40 && gt < 44) g_tc_mma[2 * (gt - 40)] = clock64();
+#endif
           mbar_wait(&S.full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef PCV_TC_TRACE
+          if (blockIdx.x == 0 && gt >= 40 && gt < 44) g_tc_mma[2 * (gt - 40) + 1] = clock64();
+#endif
           if (gt == 0) TC_TRACE(4);
           umma_tf32(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC, 0);
           umma_commit(&S.empty[s]);
@@ -292,7 +299,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         const uint32_t buf = gt & 1;
         mbar_wait_u32(tfull_u32 + buf * 8, (gt >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (threadIdx.x == 64 && gt < 8) TC_TRACE(5 + gt);
+        if (threadIdx.x == 64 && gt >= 40 && gt < 44) TC_TRACE(5 + 2 * (gt - 40));
         const uint32_t taddr = taddr0 + buf * TC_BN;
         uint32_t va[32], vb[32];
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
@@ -328,6 +335,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
+        if (threadIdx.x == 64 && gt >= 40 && gt < 44) TC_TRACE(6 + 2 * (gt - 40));
       }
       if (live) {
         // hand the surviving chunks of this (slot, slice) stream to the refine kernel
@@ -361,6 +369,9 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
 #ifdef PCV_TC_TRACE
 extern "C" int pcv_debug_tc_trace(long long *host16) {
   return (int)cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(long long) * 16);
+}
+extern "C" int pcv_debug_tc_mma(long long *host16) {
+  return (int)cudaMemcpyFromSymbol(host16, g_tc_mma, sizeof(long long) * 16);
 }
 extern "C" int pcv_debug_tc_cta(long long *host4x256) {
   return (int)cudaMemcpyFromSymbol(host4x256, g_tc_cta, sizeof(long long) * 4 * 256);

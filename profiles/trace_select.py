@@ -1,7 +1,7 @@
 """Phase trace of the tcgen05 filter kernel (CTA 0, clock64): builds a SEPARATE library with
 -DPCV_TC_TRACE under profiles/_trace/ (never the shipped one) and prints the cycle offsets of
   0 entry | 1 setup done (barriers, TMEM alloc) | 2 query tile staged | 3 first TMA issued |
-  4 first MMA issued | 5..12 epilogue sees tile 0..7 | 13 segment handed over | 14 TMEM freed
+  4 first MMA issued | 5+2k / 6+2k epilogue warp 2 sees / releases tile 40+k | 13 segment handed over | 14 TMEM freed
     python profiles/trace_select.py 2048x128 50000x10240"""
 import ctypes
 import os
@@ -39,6 +39,13 @@ for shp in [a for a in sys.argv[1:] if "x" in a] or ["2048x128"]:
     _lib.load().pcv_debug_tc_trace(t)
     t = list(t)
     print(shp, " ".join("%d:%d" % (i, t[i] - t[0]) for i in range(15)), flush=True)
+    mm = (ctypes.c_longlong * 16)()
+    _lib.load().pcv_debug_tc_mma(mm)
+    mm = list(mm)
+    print("   steady state (tiles 40-43, cycles from kernel entry): epilogue warp 2 [tile visible, tile released] "
+          + " ".join("[%d,%d]" % (t[5 + 2 * k] - t[0], t[6 + 2 * k] - t[0]) for k in range(4))
+          + " | MMA issuer [TMEM buffer free, operands ready] "
+          + " ".join("[%d,%d]" % (mm[2 * k] - t[0], mm[2 * k + 1] - t[0]) for k in range(4)), flush=True)
     c = (ctypes.c_longlong * 1024)()
     _lib.load().pcv_debug_tc_cta(c)
     c = list(c)
