@@ -472,11 +472,12 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
       for (int nb = (int)crank * MLPC_BN; nb < L.n_out; nb += MLPC_CL * MLPC_BN) {
         const int nbw = mlpc_nbw(L.n_out, nb);
         const bool active = lane * CT < nbw;   // lanes past the (padded) block only keep the ring moving
-        float acc[RT][CT];
+        // accumulators as fp32x2 pairs of adjacent rows: acc2[p][c] = (row 2p, row 2p+1) of column c
+        unsigned long long acc2[RT / 2][CT];
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
+        for (int r = 0; r < RT / 2; ++r)
 #pragma unroll
-          for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
+          for (int c = 0; c < CT; ++c) acc2[r][c] = 0ull;
         for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
           const int s = g % MLPC_STAGES;
           mbar_wait(&full[s], (g / MLPC_STAGES) & 1);
@@ -489,14 +490,17 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
               const float2 w2 = *reinterpret_cast<const float2 *>(ws + kk * nbw);
               w[0] = w2.x; w[1] = w2.y;
             };
+            // 4 FFMA2 per k-step: (rows 0,1 | rows 2,3) x (column 0 | column 1), the weight broadcast to both halves
             auto fma_ops = [&](const float (&a)[RT], const float (&w)[CT]) {
-#pragma unroll
-              for (int r = 0; r < RT; ++r)
-#pragma unroll
-                for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(a[r], w[c], acc[r][c]);
+              const unsigned long long a01 = pack2(a[0], a[1]), a23 = pack2(a[2], a[3]);
+              const unsigned long long w0 = pack2(w[0], w[0]), w1 = pack2(w[1], w[1]);
+              ffma2(acc2[0][0], a01, w0);
+              ffma2(acc2[0][1], a01, w1);
+              ffma2(acc2[1][0], a23, w0);
+              ffma2(acc2[1][1], a23, w1);
             };
             // two warps per scheduler: the operands of the next three k-steps are in flight while
-            // this step's 8 FMAs issue
+            // this step's FMAs issue
             float a0[RT], a1[RT], a2[RT], a3[RT], w0[CT], w1[CT], w2[CT], w3[CT];
             load_ops(0, a0, w0);
             load_ops(1, a1, w1);
@@ -516,6 +520,11 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);   // this warp is done reading the stage
         }
+        float acc[RT][CT];
+#pragma unroll
+        for (int r = 0; r < RT / 2; ++r)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) unpack2(acc2[r][c], acc[2 * r][c], acc[2 * r + 1][c]);
         // bias + activation -> the next layer's buffer of all four CTAs (+ HBM); padded columns -> 0
 #pragma unroll
         for (int c = 0; c < CT; ++c) {

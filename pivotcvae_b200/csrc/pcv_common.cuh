@@ -55,6 +55,21 @@ struct Table {
     pcv::count_launch();                                                          \
   } while (0)
 
+// Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fused multiply-adds per instruction on
+// 64-bit register pairs, bit-identical to two fmaf().  A {w, w} pair compiles to the instruction's
+// scalar-broadcast operand form, so pairing costs no extra instructions.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 // ---------------------------------------------------------------------------
 // Portable transcendental: the same sequence of IEEE operations is restated in
 // oracle/pcv_oracle.c, so exp() agrees bit for bit between the CUDA path and
