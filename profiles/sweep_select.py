@@ -6,6 +6,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("PCV_LIB"):          # A/B runs: load another build of the library
+    from pivotcvae_b200 import _lib
+    _lib.LIB_PATH = os.environ["PCV_LIB"]
 from pivotcvae_b200 import ops  # noqa: E402
 
 g = torch.Generator(device="cuda").manual_seed(0)
