@@ -25,7 +25,6 @@
 
 namespace pcv {
 
-constexpr int MLP_THREADS = 256;
 constexpr int MLP_KC = 32;    // k-chunk staged per step
 constexpr int MLP_NB = 256;   // output columns per pass
 constexpr int MLP_WLD_MAX = MLP_NB + 4;   // stage row stride: 257 (CT=1, conflict-free transposing stores) or 260

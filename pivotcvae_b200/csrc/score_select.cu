@@ -233,21 +233,22 @@ score_select_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_off
     __syncthreads();
   }
 
-  if (MODE == SS_LOGITS) return;
-  // lanes saw disjoint, increasing item sets: merge with lowest-index ties
+  if constexpr (MODE != SS_LOGITS) {
+    // lanes saw disjoint, increasing item sets: merge with lowest-index ties
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    float v = best[r];
-    int32_t ix = bidx[r];
+    for (int r = 0; r < R; ++r) {
+      float v = best[r];
+      int32_t ix = bidx[r];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, v, o);
-      int32_t oi = __shfl_xor_sync(0xffffffffu, ix, o);
-      if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
-    }
-    if (lane == 0 && row0 + r < M) {
-      part_val[(int64_t)blockIdx.y * M + row0 + r] = v;
-      part_idx[(int64_t)blockIdx.y * M + row0 + r] = ix;
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int32_t oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+      }
+      if (lane == 0 && row0 + r < M) {
+        part_val[(int64_t)blockIdx.y * M + row0 + r] = v;
+        part_idx[(int64_t)blockIdx.y * M + row0 + r] = ix;
+      }
     }
   }
 }

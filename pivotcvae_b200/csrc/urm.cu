@@ -15,7 +15,6 @@
 namespace pcv {
 
 constexpr int URM_MAX_L = 16;
-constexpr int URM_MAX_D = 32;
 
 template <int D>
 __global__ void __launch_bounds__(128)
