@@ -253,7 +253,11 @@ def run_train(args, w):
     model, _ = build_gpu(w, sd, env_sd, "greedy", device)
     model.noise.reseed(99 + rank)
     model.ce_engine = args.ce_engine
+    # the reduced-precision training config (tf32 CE engine) also lets cuBLAS run the MLP backward GEMMs
+    # on the tensor cores in tf32; the exact engine keeps fp32 SIMT GEMMs
     n_neg = w["n_items"] if args.n_neg <= 0 else args.n_neg
+    tf32_bwd = args.ce_engine == "tf32" and n_neg >= w["n_items"]
+    torch.backends.cuda.matmul.allow_tf32 = tf32_bwd
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=(world == 1))
     params = [p for p in model.parameters() if p.requires_grad]
     batches = [make_train_batch(w, B, i, seed=4321 + 7919 * rank) for i in range(K + W)]
@@ -353,9 +357,10 @@ def run_train(args, w):
     ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
     line = {"metric": "train samples/sec (PivotCVAE gt, fused catalog CE + KL, fwd+bwd+Adam)", "value": total / (ms / 1e3),
             "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 logits, f32 accumulate" if (args.ce_engine == "tf32" and keep >= 1.0) else "f32"),
+            "scaling": "weak", "vs_baseline": None, "dtype": ("tf32 logits and MLP-gradient GEMMs, f32 accumulate" if tf32_bwd else "f32"),
             "data": "synthetic",
             "config": {"workload": w["desc"], "batch_per_gpu": B, "n_neg": n_neg, "beta": 0.001, "ce_engine": args.ce_engine,
+                       "mlp_backward_gemm": "cuBLAS tf32" if tf32_bwd else "cuBLAS fp32",
                        "parallelism": "dp%d (replicated table, grad all-reduce)" % world,
                        "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed"},
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": "samples/s",

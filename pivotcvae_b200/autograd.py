@@ -41,10 +41,11 @@ class MlpSpec:
 
 
 def _act_grad(g, a_out, act):
+    """d/d(pre-activation) from the saved post-activation output (same sign for both activations): one kernel."""
     if act == L.ACT_LEAKY:
-        return g * torch.where(a_out > 0, 1.0, 0.01)
+        return torch.ops.aten.leaky_relu_backward(g, a_out, 0.01, True)
     if act == L.ACT_RELU:
-        return g * (a_out > 0).to(g.dtype)
+        return torch.ops.aten.threshold_backward(g, a_out, 0.0)
     return g
 
 
