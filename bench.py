@@ -551,7 +551,7 @@ def run_ours(args, w):
     flops = 2.0 * D * N * (B * L_)
     ach = flops / (dom["ms_avg"] * 1e-3) / 1e12
     tc = args.engine in ("auto", "tcgen05") and D == 8 and N >= 2048 and mode != "sampled_all"
-    kname = ("score_select_tc_kernel (tcgen05 tf32 filter) + tc_overflow + tc_refine (exact fp32)" if tc
+    kname = ("score_select_tc_kernel (tcgen05 tf32 filter) + tc_refine (exact fp32)" if tc
              else "score_select_kernel<D=%d> (exact fp32 SIMT) + finalize" % D)
     roofline = {"bound": "tensor", "kernel": "%s, M=%d rows x N=%d items" % (kname, B * L_, N),
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
@@ -563,7 +563,7 @@ def run_ours(args, w):
                                       "frac": (B * L_) * N / (dom["ms_avg"] * 1e-3) / (64 * 148 * 1.965e9)},
                 "logits_per_s": (B * L_) * N / (dom["ms_avg"] * 1e-3),
                 "engine": args.engine, "share_of_step": dom["ms_avg"] / (ms / K) if dom["calls"] else None,
-                "timing": ("CUDA events around a graph replay of the call alone (its 3 kernels) on the decoder's queries, L2 flushed, "
+                "timing": ("CUDA events around a graph replay of the call alone (its 2 kernels) on the decoder's queries, L2 flushed, "
                            "%d replays after the timed region; eager launch of the same call: %.4f ms" % (KP, eager_ms)) if dom_graph_ms is not None
                           else "CUDA events around the eager launch of the same call, %d steps after the timed region" % KP,
                 "per_call_ms": {k: round(v["ms_avg"], 4) for k, v in ksum.items()}}

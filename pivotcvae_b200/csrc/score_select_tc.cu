@@ -7,7 +7,7 @@
 //   1. The table handle keeps a PRE-SWIZZLED copy of the frozen table (rows with bit 2
 //      of the row index set have their two 16-byte halves swapped = the K-major
 //      SWIZZLE_32B shared-memory image).  One TMA bulk copy (cp.async.bulk, 8 KB,
-//      a single contiguous request) per 256-item tile streams it into a 16-stage
+//      a single contiguous request) per 256-item tile streams it into a 12-stage
 //      shared-memory ring.  (A 2-D tensor-map load with a 32-byte inner box was
 //      measured ~8x slower: one 32 B request per row; see profiles/.)
 //   2. One elected thread issues tcgen05.mma.kind::tf32, M=128 (query rows, staged
@@ -20,15 +20,18 @@
 //      band = 2*eps, eps = 1.25 * 2^-9 * |q|_2 * max_j |w_j|_2 bounds |tf32 - fp32 chain|
 //      (both operands truncated to 10 mantissa bits: relative 2^-10 each), so the
 //      exact arg-max (and every exact tie) is always in the list.
-//   4. Each (row, split, column-slice) stream hands its running max and its (<= 4)
+//   4. Each (row, CTA slot, column-slice) stream hands its running max and its (<= 4)
 //      surviving chunks to tc_refine_kernel: one warp per row takes R = max over the
 //      streams, and re-scores item-by-item (lane = item, coalesced 1 KB reads) every
 //      chunk still inside the band of R with the exact fp32 FMA chain from the fp32
 //      table; winner = largest exact score, ties -> lowest index.
+//   5. Chunks that do not fit a stream's lists (heavy exact ties) spill to the CTA's region
+//      of an overflow list and are re-scored exactly at the end of the filter kernel itself
+//      (packed 64-bit atomicMax per row, folded in by the refine kernel).
 //
 // The (M x N) logits never leave TMEM, and the result is exact for any input
-// (streams with more chunks inside the band than the lists hold — heavy exact
-// ties — are flagged and scanned exactly by the refine kernel).
+// (streams whose overflow region is full too are flagged and scanned exactly by the
+// refine kernel).
 #include "tc_common.cuh"
 
 namespace pcv {
@@ -63,6 +66,7 @@ struct __align__(1024) TcSmem {
   float rmax[TC_BM];                           // running max per row, shared by the column slices
   unsigned long long full[SEL_STAGES], empty[SEL_STAGES], tfull[2], tempty[2], afull[2], aempty[2];
   uint32_t tmem_base;
+  unsigned int ovf_n;                           // overflow entries this CTA has spilled to its region of the global list
 };
 
 // max of 32 accumulator values; g[0..10] are the maxima of the 3-element groups
@@ -74,6 +78,65 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[1
   g[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
   float a = max3(g[0], g[1], g[2]), b = max3(g[3], g[4], g[5]), c = max3(g[6], g[7], g[8]);
   return max3(max3(a, b, c), g[9], g[10]);
+}
+
+// Packed exact winner of a row among its overflow chunks, merged with a 64-bit atomicMax:
+// (order-preserving float bits << 32) | (0xffffffff - item) -> largest score, then lowest index.
+__device__ __forceinline__ unsigned long long pack_best(float v, int32_t j) {
+  v = v + 0.0f;  // -0 -> +0 so that equal scores compare equal
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
+}
+__device__ __forceinline__ void unpack_best(unsigned long long p, float *v, int32_t *j) {
+  uint32_t b = (uint32_t)(p >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+  *v = __uint_as_float(b);
+  *j = (int32_t)(0xffffffffu - (uint32_t)p);
+}
+
+// Append one chunk to this CTA's region of the overflow list; true when the region is full.  Out of line on
+// purpose: inlined, its address arithmetic gets hoisted into the per-chunk fast path.
+__device__ __noinline__ bool tc_spill(unsigned int *ovf_n, unsigned long long *__restrict__ ovf_ent,
+                                      int32_t *__restrict__ ovf_row, unsigned int cap, unsigned long long ent, int32_t row) {
+  const unsigned int pos = atomicAdd(ovf_n, 1u);
+  if (pos >= cap) return true;
+  const size_t o = (size_t)blockIdx.x * cap + pos;
+  ovf_ent[o] = ent;
+  ovf_row[o] = row;
+  return false;
+}
+
+// One warp per spilled chunk (lane = item): exact fp32 re-score, the winner is merged into row_best[row],
+// which tc_refine_kernel folds into the row's result.
+__device__ __noinline__ void tc_rescore_overflow(const float *__restrict__ W, int64_t n_rows, const float *__restrict__ Q,
+                                                 const unsigned long long *__restrict__ ent, const int32_t *__restrict__ rows,
+                                                 unsigned int n, unsigned long long *__restrict__ row_best) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned int i = warp; i < n; i += blockDim.x >> 5) {
+    const int64_t row = rows[i];
+    const int64_t j = (int64_t)(uint32_t)ent[i] + lane;
+    float best = -INFINITY;
+    int32_t bidx = 0x7fffffff;
+    if (j < n_rows) {
+      const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
+      const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
+      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
+      float sc = 0.f;
+      sc = fmaf(q0.x, w0.x, sc); sc = fmaf(q0.y, w0.y, sc); sc = fmaf(q0.z, w0.z, sc); sc = fmaf(q0.w, w0.w, sc);
+      sc = fmaf(q1.x, w1.x, sc); sc = fmaf(q1.y, w1.y, sc); sc = fmaf(q1.z, w1.z, sc); sc = fmaf(q1.w, w1.w, sc);
+      best = sc;
+      bidx = (int32_t)j;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (lane == 0 && bidx != 0x7fffffff) atomicMax(row_best + row, pack_best(best, bidx));
+  }
 }
 
 // Work decomposition: the (row tile, table tile) pairs form one flat sequence of n_units =
@@ -97,8 +160,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
                        const float *__restrict__ Q, int64_t M, int T, int64_t n_units,
                        float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
-                       unsigned long long *__restrict__ out_ent, unsigned int *__restrict__ ovf_count,
-                       unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cap) {
+                       unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
+                       unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cta_cap) {
   extern __shared__ unsigned char smem_raw[];
   TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -106,6 +169,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   if (threadIdx.x == 0) TC_TRACE(0);
 
   if (threadIdx.x == 0) {
+    S.ovf_n = 0u;
     for (int s = 0; s < SEL_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], SEL_EPI_WARPS);
@@ -248,12 +312,10 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       }
       int cnt = 0;
       bool ovf = false;
-      // rare: more chunks inside the band than a list holds -> append them to the global overflow
-      // buffer (exactly re-scored by tc_overflow_kernel); only if that is full too is the stream flagged
+      // rare: more chunks inside the band than a list holds -> append them to this CTA's region of the
+      // overflow list (re-scored exactly at the end of the kernel); only if that is full too is the stream flagged
       auto spill = [&](unsigned long long ent) {
-        const unsigned int pos = atomicAdd(ovf_count, 1u);
-        if (pos < ovf_cap) { ovf_ent[pos] = ent; ovf_row[pos] = (int32_t)row; }
-        else ovf = true;
+        if (tc_spill(&S.ovf_n, ovf_ent, ovf_row, ovf_cta_cap, ent, (int32_t)row)) ovf = true;
       };
       // a full list is compacted in place: chunks whose approximate maximum fell out of the
       // band of the (grown) running max can never hold the winner
@@ -358,12 +420,17 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
 
 #undef TC_SEGMENT
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __threadfence_block();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     if (lane == 0) TC_TRACE(14);
   }
+  // Exact re-score of the chunks this CTA spilled (normally none); kept out of line so that the hot loop's
+  // code layout does not depend on it
+  const unsigned int n_ovf = min(S.ovf_n, ovf_cta_cap);
+  if (n_ovf) tc_rescore_overflow(W, n_rows, Q, ovf_ent + (size_t)blockIdx.x * ovf_cta_cap, ovf_row + (size_t)blockIdx.x * ovf_cta_cap, n_ovf, row_best);
 }
 
 #ifdef PCV_TC_TRACE
@@ -377,56 +444,6 @@ extern "C" int pcv_debug_tc_cta(long long *host4x256) {
   return (int)cudaMemcpyFromSymbol(host4x256, g_tc_cta, sizeof(long long) * 4 * 256);
 }
 #endif
-
-// Exact re-score of the chunks that did not fit the per-stream lists: one warp per entry
-// (lane = item); the exact winner is merged into row_best[row] with a packed 64-bit atomicMax:
-// (order-preserving float bits << 32) | (0xffffffff - item) -> largest score, then lowest index.
-__device__ __forceinline__ unsigned long long pack_best(float v, int32_t j) {
-  v = v + 0.0f;  // -0 -> +0 so that equal scores compare equal
-  uint32_t b = __float_as_uint(v);
-  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  return ((unsigned long long)b << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
-}
-__device__ __forceinline__ void unpack_best(unsigned long long p, float *v, int32_t *j) {
-  uint32_t b = (uint32_t)(p >> 32);
-  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
-  *v = __uint_as_float(b);
-  *j = (int32_t)(0xffffffffu - (uint32_t)p);
-}
-
-__global__ void __launch_bounds__(256)
-tc_overflow_kernel(const float *__restrict__ W, int64_t n_rows, const float *__restrict__ Q,
-                   const unsigned int *__restrict__ ovf_count, const unsigned long long *__restrict__ ovf_ent,
-                   const int32_t *__restrict__ ovf_row, unsigned int ovf_cap,
-                   unsigned long long *__restrict__ row_best) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int n = min(*ovf_count, ovf_cap);
-  const unsigned int warps = gridDim.x * (blockDim.x >> 5);
-  for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
-    const int64_t row = ovf_row[i];
-    const int64_t j = (int64_t)(uint32_t)ovf_ent[i] + lane;
-    float best = -INFINITY;
-    int32_t bidx = 0x7fffffff;
-    if (j < n_rows) {
-      const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-      const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
-      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
-      float s = 0.f;
-      s = fmaf(q0.x, w0.x, s); s = fmaf(q0.y, w0.y, s); s = fmaf(q0.z, w0.z, s); s = fmaf(q0.w, w0.w, s);
-      s = fmaf(q1.x, w1.x, s); s = fmaf(q1.y, w1.y, s); s = fmaf(q1.z, w1.z, s); s = fmaf(q1.w, w1.w, s);
-      best = s;
-      bidx = (int32_t)j;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int32_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-    }
-    if (lane == 0 && bidx != 0x7fffffff) atomicMax(row_best + row, pack_best(best, bidx));
-  }
-}
 
 // Exact refine: one warp per query row.  R = max over the row's streams of their approximate
 // running maxima; every recorded chunk whose approximate maximum is >= R - band is re-scored
@@ -565,7 +582,7 @@ static void tc_plan_rows(const Table *t, int64_t M, TcPlan *p) {
   }
   p->slots = slots;
   // per (stream, row): running max (4) + count (4) + TC_OUT recorded chunks (8 each);
-  // per row: packed overflow winner (8); overflow buffer: ovf_cap x (8 + 4) + counter
+  // per row: packed overflow winner (8); overflow list: ovf_cap x (8 + 4), split evenly over the CTAs
   const size_t n_sr = (size_t)SEL_SLICES * p->slots * (size_t)M;
   p->ovf_cap = (unsigned int)(n_sr / 16 < 65536 ? 65536 : (n_sr / 16 > (1u << 24) ? (1u << 24) : n_sr / 16));
   p->var_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)p->ovf_cap * 12;
@@ -645,7 +662,7 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     return PCV_ERR_WORKSPACE;
   }
   const int64_t Mg = p.rows_per_launch;                                // rows per group (== M when it fits)
-  // fixed head (zero on entry, re-zeroed by tc_refine_kernel): overflow counter, per-row overflow winner
+  // fixed head (zero on entry, re-zeroed by tc_refine_kernel): a spare counter word, per-row overflow winner
   unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ws);
   unsigned long long *row_best = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);   // [Mg]
   unsigned long long *var = row_best + Mg;                             // per-group layout below
@@ -671,11 +688,8 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);              // [n_sr]
     int32_t *ovf_row = cc + n_sr;                                      // [ovf_cap]
     score_select_tc_kernel<<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.n_units,
-                                                                       band_scale, rr, cc, ent, ovf_count, ovf_ent,
-                                                                       ovf_row, g.ovf_cap);
-    PCV_LAUNCH_CHECK();
-    tc_overflow_kernel<<<t->sm_count, 256, 0, st>>>(t->W, t->n_rows, Qg, ovf_count, ovf_ent, ovf_row, g.ovf_cap,
-                                                    row_best);
+                                                                       band_scale, rr, cc, ent, row_best, ovf_ent,
+                                                                       ovf_row, g.ovf_cap / (unsigned)g.grid);
     PCV_LAUNCH_CHECK();
     tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.n_units, g.grid,
                                                              band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
