@@ -27,4 +27,14 @@ def install_dropin():
     sys.modules["env.response_model"] = response_model
     env_pkg.response_model = response_model
     sys.modules["train_generative"] = train_generative
+    # slate metrics (analysis.py:5-30): the reference module also holds ranking metrics that are not on the
+    # path, so an importable reference `analysis` only gets its two slate metrics replaced
+    from . import analysis as slate_metrics
+    try:
+        import analysis as ref_analysis
+    except ImportError:
+        sys.modules["analysis"] = slate_metrics
+    else:
+        ref_analysis.get_coverage = slate_metrics.get_coverage
+        ref_analysis.get_ILS = slate_metrics.get_ILS
     return models_pkg, env_pkg

@@ -148,6 +148,61 @@ def get_model(args, response_model):
     return None
 
 
+def main(args):
+    """Orchestration of train_generative.py:242-301: load the environment + datasets, build the generative
+    model, train it (one beta, or the beta grid when args.beta <= 0).
+
+    Data IO is NOT part of this package (out of scope): `data_extract`, `data_loader`, `my_utils`
+    and `settings` are the reference's own modules, imported from the reference checkout on sys.path.
+    Two slips of the reference's beta-grid branch are read as intended: the undefined `betaModelPath`
+    (:293) is the `modelPath` built two lines above it, and the bare `Logger` (:291) is `utils.Logger`."""
+    try:
+        import data_extract as dae
+        import my_utils as utils
+        import settings
+        from data_loader import UserSlateResponseDataset
+    except ImportError as e:   # pragma: no cover - depends on the host environment
+        raise ImportError("train_generative.main needs the reference's data modules (data_extract, data_loader, "
+                          "my_utils, settings) on sys.path: %s" % e)
+    logger = utils.Logger(utils.make_gen_model_path(args, "log/"))
+    if args.dataset not in ("yoochoose", "movielens"):      # simulation environment
+        respModel, trainset, valset = dae.load_simulation(args, logger)
+    else:
+        if args.dataset == "yoochoose":
+            train, val, _ = dae.read_yoochoose(entire_set=False)
+        else:
+            train, val = dae.read_movielens(entire=False)
+        trainset = UserSlateResponseDataset(train["features"], train["sessions"], train["responses"], args.nouser)
+        if args.dataset == "yoochoose":
+            trainset.balance_n_click()
+        valset = UserSlateResponseDataset(val["features"], val["sessions"], val["responses"], args.nouser)
+        respModel = torch.load(open(args.resp_path, "rb"), weights_only=False)
+    trainset.init_sampling(args.nneg)
+    valset.init_sampling(args.nneg)
+    respModel.to(args.device)
+    respModel.device = args.device
+    gen_model = get_model(args, respModel)
+    if not args.mask_train:
+        logger.log("Candidate training")
+        gen_model.candidateFlag = True
+    else:
+        logger.log("Mask training")
+    if args.beta > 0:
+        modelPath = utils.make_gen_model_path(args, "trained_gen/")
+        train_on_dataset(trainset, valset, gen_model, modelPath, logger, respModel,
+                         args.batch_size, args.epochs, args.lr, args.wdecay, args.beta)
+        return
+    logger.log("Beta test")
+    for beta in settings.BETA_LIST:
+        args.beta = beta
+        betaLogger = utils.Logger(utils.make_gen_model_path(args, "log_beta/"))
+        modelPath = utils.make_gen_model_path(args, "trained_beta/")
+        betaLogger.log("beta = " + str(beta))
+        train_on_dataset(trainset, valset, gen_model, modelPath, betaLogger, respModel,
+                         args.batch_size, args.epochs, args.lr, args.wdecay, beta)
+        logger.log("Done, model saved to: " + modelPath)
+
+
 def add_gen_model_parse(parser):
     parser.add_argument("--dim", type=int, default=8)
     parser.add_argument("--model", type=str, default="pivotcvae_gt_pi")

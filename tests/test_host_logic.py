@@ -94,8 +94,13 @@ def test_dropin_aliases_and_registry():
     picks = {k: (c.train_pick, c.infer_pick) for k, c in PIVOTCVAE_MODELS.items()}
     assert picks["pivotcvae_gt_pi"] == ("gt", "max") and picks["pivotcvae_sgt_spi"] == ("sample_gt", "sample")
     assert picks["pivotcvae_pt_spi"] == ("max", "sample") and picks["pivotcvae_spt_pi"] == ("sample", "max")
-    for name in ("downsample", "get_gen_loss", "train_on_dataset", "get_model", "add_gen_model_parse"):
+    for name in ("downsample", "get_gen_loss", "train_on_dataset", "get_model", "add_gen_model_parse", "main"):
         assert hasattr(train_generative, name)
+    import analysis
+    assert callable(analysis.get_coverage) and callable(analysis.get_ILS)
+    import argparse
+    with pytest.raises(ImportError, match="data modules"):      # data IO stays the reference's (out of scope)
+        train_generative.main(argparse.Namespace(dataset="sim"))
     # the reference's class names resolve for whole-model pickles (train_generative.py:199)
     import models.pivotcvae as mp
     for cls in ("UserPivotCVAE", "UserPivotCVAE2", "UserPivotCVAE_PrePermute", "UserPivotCVAE_PrePermute2",
