@@ -3,7 +3,6 @@
 Both run in one fused kernel pass over the recommended slates: one thread
 per slate gathers the L embedding rows, normalises them and reduces |sum_i e_i|^2; the same
 pass ORs the item ids into a coverage bitmap."""
-import ctypes
 
 import torch
 

@@ -11,7 +11,6 @@ strings; the reference's class names are kept so pickles and imports resolve.
 import torch
 
 from .. import _lib as L
-from .. import ops
 from .cvae import BaseCVAE
 
 

@@ -9,7 +9,6 @@ reference's semantics (CE mean over B*L rows, KL summed, Adam without decay).
 import numpy as np
 import torch
 
-from . import ops
 from .autograd import CatalogCEFn, KLFn  # noqa: F401
 from .env.response_model import sample_users
 from .models.listcvae import UserListCVAEWithPrior
