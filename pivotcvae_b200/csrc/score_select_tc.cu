@@ -450,7 +450,8 @@ extern "C" int pcv_debug_tc_cta(long long *host4x256) {
 // item by item (lane = item) with the exact fp32 sequential-k FMA chain; winner =
 // largest exact score, ties -> lowest index.  Streams flagged -1 (too many chunks
 // inside the band, i.e. heavy exact ties) are scanned completely.
-__global__ void __launch_bounds__(256)
+// (256, 5): 48 registers -> 40 resident warps per SM, so M = 10240 rows finish in two waves instead of three
+__global__ void __launch_bounds__(256, 5)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
                  int64_t M, int T, int64_t n_units, int G, float band_scale,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
