@@ -13,7 +13,10 @@
  *  - every op takes a cudaStream_t (as void*) and is asynchronous on it;
  *  - return 0 on success, <0 on error (pcv_last_error() gives the text);
  *  - no allocation inside ops: scratch comes from the caller through the
- *    *_workspace_bytes() queries;
+ *    *_workspace_bytes() queries.  The one exception is pcv_table_create, a
+ *    one-off constructor: it synchronises the device and allocates the handle's
+ *    packed table copies (freed by pcv_table_destroy); a failure there is an
+ *    error, never a silent downgrade to a slower engine;
  *  - float = IEEE binary32, indices = int64 (torch.long), row-major tensors.
  *  - there is no CPU fallback: a non-sm_100 device yields PCV_ERR_ARCH.
  */

@@ -132,7 +132,11 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
     memcpy(&m2, &h_max, sizeof(float));
     t->max_row_norm = sqrtf(m2) * 1.000001f;
   }
-  table_init_tc(t);
+  rc = table_init_tc(t);
+  if (rc != PCV_OK) {
+    delete t;
+    return rc;
+  }
   *out = reinterpret_cast<pcv_table *>(t);
   return PCV_OK;
 }

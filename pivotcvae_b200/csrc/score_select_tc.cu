@@ -308,7 +308,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         // never pass, +inf for dummy rows so that nothing ever passes
         r = live ? -3.0e38f : INFINITY;
         thr = r;
-        S.rmax[trow] = -3.0e38f;   // shared with the other column slice of this row (benign race: monotone max)
+        atomicExch(reinterpret_cast<unsigned int *>(&S.rmax[trow]), __float_as_uint(-3.0e38f));   // shared with the other column slices
       }
       int cnt = 0;
       bool ovf = false;
@@ -370,9 +370,11 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         // other column slices.  The slices are never more than the two TMEM buffers apart, so with >= 8 tiles
         // per exchanging segment a slice can not read a value another one published for a LATER segment.
         if (exch && t < 4) {
-          const float sh = S.rmax[trow];
+          // float max as an integer atomic: signed max for r >= 0, unsigned min for r < 0 (correct for any mix of signs)
+          const float sh = (r >= 0.f)
+              ? __int_as_float(atomicMax(reinterpret_cast<int *>(&S.rmax[trow]), __float_as_int(r)))
+              : __uint_as_float(atomicMin(reinterpret_cast<unsigned int *>(&S.rmax[trow]), __float_as_uint(r)));
           if (sh > r) { r = sh; thr = r - band; }
-          else if (r > sh) S.rmax[trow] = r;
         }
         TC_WAIT_LD(va);
         if (t < n_full) {
@@ -628,18 +630,23 @@ int table_init_tc(Table *t) {
   t->packed = nullptr;
   if (t->dim != TC_D) return PCV_OK;
   float *p = nullptr;
-  if (cudaMalloc(&p, (size_t)t->n_rows * TC_D * sizeof(float)) != cudaSuccess) {
+  cudaError_t e = cudaMalloc(&p, (size_t)t->n_rows * TC_D * sizeof(float));
+  if (e != cudaSuccess) {   // no silent downgrade to the 8x slower SIMT engine: the caller sees the failure
     cudaGetLastError();
-    return PCV_OK;  // engine stays unavailable; the SIMT engine serves
+    set_error("pcv_table_create: cudaMalloc of the pre-swizzled table copy (%zu bytes) -> %s",
+              (size_t)t->n_rows * TC_D * sizeof(float), cudaGetErrorString(e));
+    return PCV_ERR_CUDA;
   }
   const int64_t chunks = t->n_rows * 2;
   pack_sw32_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(reinterpret_cast<const float4 *>(t->W), t->n_rows,
                                                               reinterpret_cast<float4 *>(p));
   count_launch();
-  if (cudaDeviceSynchronize() != cudaSuccess) {
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
     cudaGetLastError();
     cudaFree(p);
-    return PCV_OK;
+    set_error("pcv_table_create: packing the pre-swizzled table copy -> %s", cudaGetErrorString(e));
+    return PCV_ERR_CUDA;
   }
   t->packed = p;
   t->tmap_valid = 1;
@@ -695,7 +702,15 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.n_units, g.grid,
                                                              band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
                                                              out_val ? out_val + r0 : nullptr);
-    PCV_LAUNCH_CHECK();
+    if (cudaPeekAtLastError() != cudaSuccess) {
+      // the filter ran but the kernel that re-zeroes the head did not launch: heal the workspace here, so that a
+      // failed call never poisons the next one (steady state pays nothing for this)
+      cudaError_t le = cudaGetLastError();
+      cudaMemsetAsync(ws, 0, 256 + (size_t)Mg * 8, st);
+      set_error("score_select(tcgen05): refine kernel launch -> %s (workspace head re-zeroed)", cudaGetErrorString(le));
+      return PCV_ERR_CUDA;
+    }
+    count_launch();
   }
   return PCV_OK;
 }

@@ -35,6 +35,8 @@ class GraphedSlateGenerator:
         with torch.cuda.graph(self.graph):
             self.items, self.z_mu, self.resp = self._step()
         self.launches_per_step = ops.launch_count() - l0
+        model.item_table().pin_workspaces()     # their pointers are baked into the graph
+        ops.pin_packed()
 
     def _step(self):
         items, z_mu = self.model.recommend(self.ctx, None if self.no_user else self.users, return_item=True)
@@ -80,12 +82,25 @@ class GraphedTrainStep:
             return loss.detach(), rec.detach(), kld.detach()
 
         self._step = step
+        self._params = [p for p in model.parameters() if p.requires_grad]
+        # the warm-up runs real Adam updates on the (all-zero) static batch: snapshot the parameters and the
+        # optimizer state first and put them back IN PLACE afterwards (pointers must not move before capture)
+        with torch.no_grad():
+            snap_p = [p.detach().clone() for p in self._params]
+            snap_s = [{k: v.clone() for k, v in optimizer.state.get(p, {}).items() if torch.is_tensor(v)}
+                      for p in self._params]
         model.noise.begin_graph(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 step()
+            with torch.no_grad():
+                for p, sp, ss in zip(self._params, snap_p, snap_s):
+                    p.copy_(sp)
+                    for k, v in optimizer.state.get(p, {}).items():
+                        if torch.is_tensor(v):
+                            v.copy_(ss[k]) if k in ss else v.zero_()   # state created by the warm-up starts at zero
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -93,9 +108,15 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.rec, self.kld = step()
         self.launches_per_step = ops.launch_count() - l0
+        model.item_table().pin_workspaces()
+        ops.pin_packed()
 
     def __call__(self, batch):
         for k, v in self.static.items():
             v.copy_(batch[k].reshape(v.shape), non_blocking=True)
         self.graph.replay()
+        # the replayed optimizer step changed the parameters behind autograd's back: advance their version
+        # counters so every cache keyed on them (packed weights, concatenated heads) refreshes on next use
+        for p in self._params:
+            torch.autograd.graph.increment_version(p)
         return self.loss, self.rec, self.kld

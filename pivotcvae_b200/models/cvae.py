@@ -87,12 +87,15 @@ class BaseCVAE(nn.Module):
         t = self._table
         if self._vp is not None:
             _, lo, hi = self._vp
-            if t is None or t.row_offset != lo or t.n_rows != hi - lo or t.weight.data_ptr() != w[lo:hi].data_ptr():
+            if (t is None or t.row_offset != lo or t.n_rows != hi - lo or t.weight.data_ptr() != w[lo:hi].data_ptr()
+                    or t.version != w._version):
                 t = ops.Table(w.detach()[lo:hi], row_offset=lo)
+                t.version = w._version
                 self._table = t
             return t
-        if t is None or t.weight.data_ptr() != w.data_ptr() or t.n_rows != w.shape[0]:
+        if t is None or t.weight.data_ptr() != w.data_ptr() or t.n_rows != w.shape[0] or t.version != w._version:
             t = ops.Table(w.detach())
+            t.version = w._version
             self._table = t
         return t
 
@@ -137,24 +140,6 @@ class BaseCVAE(nn.Module):
         return self.noise.stream_args(B)
 
     # ---- reference API
-    def encode(self, emb, c, u_emb=None):
-        raise NotImplementedError
-
-    def decode(self, z, c, u_emb=None):
-        raise NotImplementedError
-
-    def get_prior(self, r, u=None):
-        raise NotImplementedError
-
-    def forward(self, s, r, candidates=None, u=None):
-        raise NotImplementedError
-
-    def recommend(self, r, u=None, return_item=False):
-        raise NotImplementedError
-
-    def log(self, logger):
-        raise NotImplementedError
-
     def reparametrize(self, mu, logvar):
         """z = eps * exp(0.5*logvar) + mu (cvae.py:79-83); eps from the model's NoiseSource.
         Runs the kernel's reparameterisation epilogue behind an identity layer."""

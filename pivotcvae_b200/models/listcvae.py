@@ -61,9 +61,9 @@ class UserListCVAEWithPrior(BaseCVAE):
             r, u, _ = self._inputs(r, u)
             out, z, rx = self._prior_chain(r, u, self.decMLP)      # prior -> z -> decoder in one launch
             z_mu = out[:, :self.latent_size]
-            if return_item:
-                return self.get_recommended_item(rx), z_mu
-            return rx, z_mu
+            res = self.get_recommended_item(rx) if return_item else rx
+            self.noise.flush_eager()
+            return res, z_mu
 
     def log(self, logger):
         for k, v in (("feature size", self.feature_size), ("slate size", self.slate_size),

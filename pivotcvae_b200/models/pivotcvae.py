@@ -129,9 +129,9 @@ class UserPivotCVAE(BaseCVAE):
             user_seg = None if self.noUser else self._user_seg(u)
             rx = self._scm(z, ("onehot", r), self._pick_index(pivot_output, None), user_seg, [])
             z_mu = out[:, :self.latent_size]
-            if return_item:
-                return self.get_recommended_item(rx), z_mu
-            return rx.view(r.shape[0], self.slate_size, self.feature_size), z_mu
+            res = self.get_recommended_item(rx) if return_item else rx.view(r.shape[0], self.slate_size, self.feature_size)
+            self.noise.flush_eager()
+            return res, z_mu
 
     def log(self, logger):
         for k, v in (("feature size", self.feature_size), ("slate size", self.slate_size),

@@ -43,6 +43,13 @@ class NoiseSource:
         self.counter = 0
         return used
 
+    def flush_eager(self):
+        """End of an EAGER top-level op (recommend / get_gen_loss) while graph mode is installed: advance the
+        device counter by the rows this op drew, exactly as the captured step's last node does, so eager calls
+        and graph replays never reuse a Philox row."""
+        if self.device_counter is not None and self.counter and not torch.cuda.is_current_stream_capturing():
+            self.end_graph_step()
+
     def push(self, kind, tensor):
         self._queue[kind].append(tensor)
 

@@ -105,7 +105,8 @@ class Table:
         with torch.cuda.device(self.weight.device):
             L.check(L.load().pcv_table_create(_ptr(self.weight), self.n_rows, self.dim, self.row_offset,
                                               ctypes.byref(self._h)), "pcv_table_create")
-        self._ws = {}
+        self._ws = collections.OrderedDict()
+        self.version = None     # set by the owner: version counter of the weight the handle snapshotted
 
     def __del__(self):
         try:
@@ -122,15 +123,30 @@ class Table:
     def workspace(self, kind, M):
         key = (kind, int(M))
         ws = self._ws.get(key)
+        if ws is not None:
+            self._ws.move_to_end(key)
         if ws is None:
             n = ctypes.c_size_t()
             fn = L.load().pcv_score_select_workspace_bytes if kind == "select" else L.load().pcv_ce_workspace_bytes
             L.check(fn(self._h, int(M), ctypes.byref(n)), "workspace query")
             ws = torch.zeros(max(int(n.value), 256), dtype=torch.uint8, device=self.weight.device)  # zero-filled once (ABI contract)
-            if len(self._ws) > 16:
-                self._ws.clear()
+            # least-recently-used eviction, one entry at a time; a workspace whose pointer a live CUDA graph
+            # baked in is pinned by that graph object (pin_workspaces) and is never dropped
+            while len(self._ws) >= self.WS_MAX:
+                victim = next((k for k in self._ws if k not in self._pinned), None)
+                if victim is None:
+                    break
+                del self._ws[victim]
             self._ws[key] = ws
         return ws
+
+    WS_MAX = 16
+    _pinned = frozenset()
+
+    def pin_workspaces(self):
+        """Called by the Graphed* objects after capture: every workspace allocated so far stays alive
+        (and is never evicted) for the lifetime of this table handle."""
+        self._pinned = frozenset(self._pinned | set(self._ws))
 
 
 def normalize_rows(W):
@@ -255,6 +271,13 @@ class Gather:
 # another tensor while it is cached.
 _PACKED = collections.OrderedDict()   # data_ptr -> [version, shape, storage, packed, weight]
 _PACKED_MAX = 512
+_PACKED_PINNED = set()                # keys a live CUDA graph reads through: never evicted
+
+
+def pin_packed():
+    """Called by the Graphed* objects after capture: the packed copies that exist now were baked into a
+    graph as raw pointers, so they are exempt from the cache's eviction."""
+    _PACKED_PINNED.update(_PACKED.keys())
 
 
 def _pack_into(W, packed):
@@ -278,7 +301,10 @@ def packed_weight(W):
     if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not outlive its graph in the cache
         _PACKED[key] = [W._version, tuple(W.shape), W.untyped_storage(), packed, W]
         while len(_PACKED) > _PACKED_MAX:
-            _PACKED.popitem(last=False)
+            victim = next((k for k in _PACKED if k not in _PACKED_PINNED), None)
+            if victim is None:
+                break
+            del _PACKED[victim]
     return packed
 
 

@@ -48,6 +48,7 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
         tpos = _as_tensor(batch_data["sample_targets"], torch.int64, dev).reshape(-1)
         recLoss = CandidateCEFn.apply(rx.reshape(M, -1), model.item_table(), cand, tpos)
         KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
+        model.noise.flush_eager()
         return recLoss + beta * KLD, recLoss, KLD
     if getattr(model, "_vp", None) is not None:
         raise NotImplementedError("vocab-parallel training (CE partials + dQ all-reduce) is not built yet; "
@@ -66,6 +67,7 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
                                       kw["offset"], kw.get("offset_dev"), getattr(model, "ce_engine", "exact"))
     KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
     loss = recLoss + beta * KLD
+    model.noise.flush_eager()
     return loss, recLoss, KLD
 
 
