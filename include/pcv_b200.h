@@ -111,6 +111,11 @@ int pcv_philox_exponential(uint64_t seed, uint64_t offset, int64_t M, int64_t n_
  * shards in shard order; winner = max val, ties -> lowest global index. */
 int pcv_vp_merge_select(const float *vals, const int64_t *idx, int G, int64_t M,
                         int64_t *out_idx, float *out_val, pcv_stream_t stream);
+/* The same merge as ONE all-reduce: keys[i] = int64 whose SIGNED maximum over the shards is the winner
+ * (largest value, equal values -> lowest global index < 2^32).  The caller runs
+ * all_reduce(keys, MAX) (NCCL, int64) between pack and unpack; nothing else crosses NVLink. */
+int pcv_vp_pack_keys(const float *vals, const int64_t *idx, int64_t M, int64_t *keys, pcv_stream_t stream);
+int pcv_vp_unpack_keys(const int64_t *keys, int64_t M, int64_t *out_idx, float *out_val, pcv_stream_t stream);
 
 /* ------------------------------------------------------------------ */
 /* Fused MLP blocks (encoder / prior / PSM / SCM / ListCVAE decoder /  */

@@ -41,6 +41,16 @@ def _digest():
     return h.hexdigest()
 
 
+def kernel_digest(source):
+    """Digest of one kernel source + the shared headers + the flags: ties an ncu capture to the build it was taken on."""
+    h = hashlib.sha256()
+    for f in (source, "tc_common.cuh", "pcv_common.cuh"):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def build(force=False, verbose=False):
     """Compile every .cu for sm_100a and link the shared library. Returns its path."""
     dig = _digest()

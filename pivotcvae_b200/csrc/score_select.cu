@@ -287,6 +287,31 @@ __global__ void vp_merge_kernel(const float *__restrict__ vals, const int64_t *_
   if (out_val) out_val[i] = v;
 }
 
+// Vocab-parallel exchange as ONE all-reduce(MAX) on int64 keys: key = (order-preserving float bits << 32) |
+// (0xffffffff - global index), top bit flipped so that the SIGNED 64-bit maximum is: largest value first,
+// equal values -> lowest global index (the reference's tie rule).
+__global__ void vp_pack_keys_kernel(const float *__restrict__ vals, const int64_t *__restrict__ idx, int64_t M,
+                                    long long *__restrict__ keys) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float v = vals[i] + 0.0f;   // -0 -> +0: equal scores must compare equal
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const unsigned long long k = ((unsigned long long)b << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx[i]);
+  keys[i] = (long long)(k ^ 0x8000000000000000ull);
+}
+
+__global__ void vp_unpack_keys_kernel(const long long *__restrict__ keys, int64_t M, int64_t *__restrict__ out_idx,
+                                      float *__restrict__ out_val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const unsigned long long k = (unsigned long long)keys[i] ^ 0x8000000000000000ull;
+  uint32_t b = (uint32_t)(k >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+  out_idx[i] = (int64_t)(0xffffffffu - (uint32_t)k);
+  if (out_val) out_val[i] = __uint_as_float(b);
+}
+
 __global__ void philox_exponential_kernel(uint64_t seed, uint64_t offset, int64_t M,
                                           int64_t n_cols, int64_t col_offset,
                                           float *__restrict__ out) {
@@ -448,6 +473,28 @@ int pcv_philox_exponential(uint64_t seed, uint64_t offset, int64_t M, int64_t n_
   int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   philox_exponential_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(seed, offset, M, n_cols,
                                                                       col_offset, out);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+int pcv_vp_pack_keys(const float *vals, const int64_t *idx, int64_t M, int64_t *keys, pcv_stream_t stream) {
+  PCV_CHECK_ARG(vals && idx && keys, "NULL pointer");
+  PCV_CHECK_ARG(M > 0, "M must be > 0");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  vp_pack_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals, idx, M,
+                                                                                     reinterpret_cast<long long *>(keys));
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+int pcv_vp_unpack_keys(const int64_t *keys, int64_t M, int64_t *out_idx, float *out_val, pcv_stream_t stream) {
+  PCV_CHECK_ARG(keys && out_idx, "NULL pointer");
+  PCV_CHECK_ARG(M > 0, "M must be > 0");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  vp_unpack_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long *>(keys), M, out_idx, out_val);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }

@@ -220,6 +220,25 @@ def vp_merge_select(vals, idx):
     return oi, ov
 
 
+def vp_pack_keys(vals, idx):
+    """(val f32[M], global idx int64[M]) -> int64[M] keys whose signed MAX over shards is the winner."""
+    vals, idx = _f32(vals, "vals"), _i64(idx, "idx")
+    keys = torch.empty(vals.shape[0], dtype=torch.int64, device=vals.device)
+    with torch.cuda.device(vals.device):
+        L.check(L.load().pcv_vp_pack_keys(_ptr(vals), _ptr(idx), vals.shape[0], _ptr(keys), _stream()), "pcv_vp_pack_keys")
+    return keys
+
+
+def vp_unpack_keys(keys):
+    keys = _i64(keys, "keys")
+    M = keys.shape[0]
+    oi = torch.empty(M, dtype=torch.int64, device=keys.device)
+    ov = torch.empty(M, dtype=torch.float32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        L.check(L.load().pcv_vp_unpack_keys(_ptr(keys), M, _ptr(oi), _ptr(ov), _stream()), "pcv_vp_unpack_keys")
+    return oi, ov
+
+
 # ----------------------------------------------------------------------------
 # fused MLP block
 # ----------------------------------------------------------------------------

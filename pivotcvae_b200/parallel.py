@@ -6,9 +6,11 @@ Two ways the path shards, both one process per GPU over torch.distributed:
   inference needs NO collective (bench.py --gpus N, weak scaling);
 * vocab-parallel — each rank owns a contiguous, 128-aligned row range of the item
   table; every rank runs the tiny MLPs redundantly on identical inputs/noise, the
-  fused score+select runs on the local shard, and ONE small all-gather of the
-  per-row partial winners (val f32, global idx i64) per scoring step is merged with
-  the reference's tie rule (largest value, equal values -> lowest global index).
+  fused score+select runs on the local shard, and ONE small collective per scoring
+  step merges the per-row partial winners (val f32, global idx) with the reference's
+  tie rule (largest value, equal values -> lowest global index): on GPUs an
+  all-reduce(MAX) of order-preserving int64 keys, on the gloo test path an
+  all-gather + merge.
 
 The host logic here is backend-agnostic so that the gloo/CPU tests can exercise the
 exchange + merge with a stand-in local scorer.
@@ -58,8 +60,16 @@ class VocabParallelSelector:
         world = dist.get_world_size(self.group)
         if world == 1:
             return idx, val
+        if val.is_cuda and self.merge is None:
+            # ONE collective per scoring step and nothing else: (val, idx) -> order-preserving int64 key,
+            # all-reduce(MAX) over NVLink (in-switch where NCCL picks NVLS), key -> (idx, val).  Capturable
+            # in the step's CUDA graph.
+            from . import ops
+            keys = ops.vp_pack_keys(val, idx)
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=self.group)
+            return ops.vp_unpack_keys(keys)
         M = idx.shape[0]
-        # one collective per scoring step: pack (val, idx) into a single int64 buffer
+        # backend-agnostic path (gloo / CPU tests): all-gather of (val, idx) packed in one int64 buffer + merge
         packed = torch.empty(2, M, dtype=torch.int64, device=idx.device)
         packed[0] = val.view(torch.int32).to(torch.int64)
         packed[1] = idx
@@ -68,13 +78,7 @@ class VocabParallelSelector:
         out = flat.view(world, 2, M)
         vals = out[:, 0].to(torch.int32).view(torch.float32)
         idxs = out[:, 1].contiguous()
-        merge = self.merge
-        if merge is None:
-            if vals.is_cuda:
-                from . import ops
-                merge = ops.vp_merge_select
-            else:
-                merge = merge_partials
+        merge = self.merge or merge_partials
         return merge(vals.contiguous(), idxs)
 
 

@@ -194,10 +194,14 @@ def test_vocab_parallel_gloo_world2(tmp_path):
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints the contract line."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref on the host cores when that copy
+    exists, else the oracle port) prints the contract line, with the SAME config dict as the GPU arm would."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
                           "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "models", "pivotcvae.py"))
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["config"] == {"workload": line["config"]["workload"], "batch": 64, "mode": "greedy", "model": "PivotCVAE gt_pi"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "slates/s"
