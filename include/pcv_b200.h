@@ -107,6 +107,16 @@ int pcv_score_logits(const pcv_table *t, const float *Q, int64_t M, float *out,
  * out[M, n_rows]; test hook for the Philox path. */
 int pcv_philox_exponential(uint64_t seed, uint64_t offset, int64_t M, int64_t n_cols,
                            int64_t col_offset, float *out, pcv_stream_t stream);
+/* Throughput-mode sampled pivot (pivotcvae.py:349-351 and the other *_spi / spt / sgt variants):
+ * out_idx[i] ~ Categorical(sigmoid(<q_i, w_j>) / sum_j) over the WHOLE catalog, drawn exactly by rejection
+ * (uniform proposal, accept with sigmoid(s_j) / sigmoid(|q_i| max_j|w_j|)): ~2 proposals per row instead of one
+ * exponential per (row, item).  Philox4x32-10(seed, row + offset [+ *offset_dev]); every operation is portable
+ * IEEE, so the oracle reproduces the draws bit for bit.  The table must be the full catalog (row_offset 0).
+ * out_iters (optional): proposals used per row, -1 = inverse-CDF fallback after 1024 rejections.
+ * Parity mode (caller-supplied torch noise) stays pcv_score_select(PCV_SELECT_EXPRACE, noise). */
+int pcv_sigmoid_categorical(const pcv_table *t, const float *Q, int64_t M, uint64_t seed, uint64_t offset,
+                            const uint64_t *offset_dev, int64_t *out_idx, int32_t *out_iters,
+                            pcv_stream_t stream);
 /* Vocab-parallel merge: vals/idx are [G, M] partials gathered from G
  * shards in shard order; winner = max val, ties -> lowest global index. */
 int pcv_vp_merge_select(const float *vals, const int64_t *idx, int G, int64_t M,

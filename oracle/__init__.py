@@ -157,6 +157,17 @@ def score_select(W, Q, mode="greedy", noise=None):
     return idx, val
 
 
+def sigmoid_categorical(W, Q, seed, offset=0):
+    """Throughput-mode draw from Categorical(sigmoid(Q W^T)) (pivotcvae.py:349-351): the rejection sampler of
+    csrc/sampler.cu restated -> (idx int64[M], proposals used int32[M], -1 = inverse-CDF fallback)."""
+    W, Q = _f32(W), _f32(Q)
+    M = Q.shape[0]
+    idx = np.empty(M, dtype=np.int64)
+    iters = np.empty(M, dtype=np.int32)
+    lib().orc_sigmoid_categorical(_p(W), I64(W.shape[0]), I32(W.shape[1]), _p(Q), I64(M), U64(seed), U64(offset), _p(idx), _p(iters))
+    return idx, iters
+
+
 def score_logits(W, Q):
     W, Q = _f32(W), _f32(Q)
     out = np.empty((Q.shape[0], W.shape[0]), dtype=np.float32)

@@ -297,6 +297,65 @@ void orc_score_select(const float *W, int64_t N, int D, const float *Q, int64_t 
   free(Wt);
 }
 
+/* ---- pivotcvae.py:349-351 (and the other sampled variants): samp = Categorical(sigmoid(scores)).sample()
+ *      in throughput mode: exact rejection sampling, restating pivotcvae_b200/csrc/sampler.cu operation by
+ *      operation (Philox proposal `it` of row r -> (x, y, z, w); j = hi64((x:y) * N), void when
+ *      lo64 < 2^64 mod N; accept iff z < (u64)(min(sigmoid(s_j) / sigma_b, 1) * 2^32);
+ *      sigma_b = sigmoid(|q| * max_j|w_j| * 1.0001 + 1e-6); after 1024 proposals: inverse CDF in double). ---- */
+static inline float orc_sigmoidf_(float x) { return 1.0f / (1.0f + orc_expf_(-x)); }
+static inline float orc_chain_(const float *q, const float *w, int D) {
+  float s = 0.f;
+  for (int k = 0; k < D; ++k) s = fmaf(q[k], w[k], s);
+  return s;
+}
+void orc_sigmoid_categorical(const float *W, int64_t N, int D, const float *Q, int64_t M, uint64_t seed,
+                             uint64_t offset, int64_t *out_idx, int32_t *out_iters) {
+  float m2 = 0.f;
+  for (int64_t j = 0; j < N; ++j) {
+    float ss = orc_chain_(W + j * D, W + j * D, D);
+    if (ss > m2) m2 = ss;
+  }
+  const float max_row_norm = sqrtf(m2) * 1.000001f;   /* pcv_table_create */
+  const uint64_t lemire_t = (0ull - (uint64_t)N) % (uint64_t)N;
+  for (int64_t i = 0; i < M; ++i) {
+    const float *q = Q + i * D;
+    const float sigma_b = orc_sigmoidf_(sqrtf(orc_chain_(q, q, D)) * max_row_norm * 1.0001f + 1e-6f);
+    const uint64_t r = (uint64_t)i + offset;
+    int64_t pick = -1;
+    uint32_t w0 = 0;
+    for (int it = 0; it < 1024 && pick < 0; ++it) {
+      uint32_t ctr[4] = {(uint32_t)it, (uint32_t)r, (uint32_t)(r >> 32), 4u};
+      uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+      uint32_t o[4];
+      orc_philox4x32_10(ctr, key, o);
+      if (it == 0) w0 = o[3];
+      const uint64_t u = ((uint64_t)o[0] << 32) | o[1];
+      const unsigned __int128 m = (unsigned __int128)u * (uint64_t)N;
+      const int64_t j = (int64_t)(uint64_t)(m >> 64);
+      if ((uint64_t)m < lemire_t) continue;
+      const float ratio = fminf(orc_sigmoidf_(orc_chain_(q, W + j * D, D)) / sigma_b, 1.0f);
+      const uint64_t thr = (uint64_t)(ratio * 4294967296.0f);
+      if ((uint64_t)o[2] < thr) {
+        pick = j;
+        if (out_iters) out_iters[i] = it + 1;
+      }
+    }
+    if (pick < 0) {
+      double total = 0.0;
+      for (int64_t j = 0; j < N; ++j) total += (double)orc_sigmoidf_(orc_chain_(q, W + j * D, D));
+      const double target = ((double)w0 + 0.5) * (1.0 / 4294967296.0) * total;
+      double acc = 0.0;
+      pick = N - 1;
+      for (int64_t j = 0; j < N; ++j) {
+        acc += (double)orc_sigmoidf_(orc_chain_(q, W + j * D, D));
+        if (acc >= target) { pick = j; break; }
+      }
+      if (out_iters) out_iters[i] = -1;
+    }
+    out_idx[i] = pick;
+  }
+}
+
 /* ---- pivotcvae.py:274 / listcvae.py:166  p = mm(prox_emb, table.t()) ---- */
 void orc_score_logits(const float *W, int64_t N, int D, const float *Q, int64_t M, float *out) {
   for (int64_t i = 0; i < M; ++i)

@@ -26,6 +26,7 @@ struct Table {
   float *packed;
   int tmap_valid;  // 1 when the tcgen05 engine can serve this table
   float max_row_norm;  // max_j |w_j|_2 (error bound of the tf32 filter)
+  int tc_chunk_tiles;  // tcgen05 filter: tiles per column chunk once the table outgrows the L2
 };
 
 #define PCV_CHECK_ARG(cond, msg)                              \

@@ -32,6 +32,8 @@
 // The (M x N) logits never leave TMEM, and the result is exact for any input
 // (streams whose overflow region is full too are flagged and scanned exactly by the
 // refine kernel).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace pcv {
@@ -158,7 +160,7 @@ __host__ __device__ __forceinline__ int tc_cta_of(int64_t x, int64_t n_units, in
 //   warps 2+: epilogue (thread = query row x column slice).
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
-                       const float *__restrict__ Q, int64_t M, int T, int64_t n_units,
+                       const float *__restrict__ Q, int64_t M, int T, int Tc, int row_tiles, int slots_max,
                        float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
                        unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                        unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cta_cap) {
@@ -187,20 +189,31 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   const uint32_t tmem = S.tmem_base;
   if (threadIdx.x == 0) TC_TRACE(1);
 
-  const int64_t u_begin = tc_cta_begin(blockIdx.x, n_units, gridDim.x);
-  const int64_t u_end = tc_cta_begin(blockIdx.x + 1, n_units, gridDim.x);
-  // segment starting at unit u: row tile rt, table tiles [ct0, ct0 + n_tiles)
+  // COLUMN CHUNKS: a catalog that does not fit the L2 is walked chunk by chunk (Tc tiles = 32 MB each); inside a
+  // chunk the (row tile, table tile) units are cut evenly over the CTAs as before.  All CTAs are therefore in the
+  // same chunk at (about) the same time and share its tiles through the L2 instead of each streaming the whole
+  // table from HBM (C5, 10 M items: 1.9 T -> ~13 T logits/s).  T <= Tc: one chunk, the original partition.
+  const int n_chunks = (T + Tc - 1) / Tc;
+#define TC_CHUNK(ch)                                                                                   \
+  const int Tch = min(Tc, T - (ch) * Tc);                                                              \
+  const int64_t n_units = (int64_t)row_tiles * Tch;                                                    \
+  const int64_t u_begin = tc_cta_begin(blockIdx.x, n_units, gridDim.x);                                \
+  const int64_t u_end = tc_cta_begin(blockIdx.x + 1, n_units, gridDim.x);                              \
+  const int tile0 = (ch) * Tc; /* first table tile of the chunk */
+  // segment starting at unit u: row tile rt, table tiles tile0 + [ct0, ct0 + n_tiles)
 #define TC_SEGMENT(u)                                                            \
-  const int rt = (int)((u) / T);                                                 \
-  const int ct0 = (int)((u) - (int64_t)rt * T);                                  \
-  const int n_tiles = (int)min((int64_t)(T - ct0), u_end - (u));                 \
-  const int64_t j_begin = (int64_t)ct0 * TC_BN;                                  \
-  const int64_t j_end = min(n_rows, (int64_t)(ct0 + n_tiles) * TC_BN);
+  const int rt = (int)((u) / Tch);                                               \
+  const int ct0 = (int)((u) - (int64_t)rt * Tch);                                \
+  const int n_tiles = (int)min((int64_t)(Tch - ct0), u_end - (u));               \
+  const int64_t j_begin = (int64_t)(tile0 + ct0) * TC_BN;                        \
+  const int64_t j_end = min(n_rows, (int64_t)(tile0 + ct0 + n_tiles) * TC_BN);
 
   if (warp == 0) {
     // ---------------- producer: A tile of the item, then its table tiles ----------------
     uint32_t gt = 0;   // tiles issued so far (ring position)
     int it = 0;        // items started so far
+    for (int ch = 0; ch < n_chunks; ++ch) {
+    TC_CHUNK(ch)
     for (int64_t u = u_begin; u < u_end; ++it) {
       TC_SEGMENT(u)
       u += n_tiles;
@@ -243,11 +256,14 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       }
       __syncwarp();
     }
+    }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       uint32_t gt = 0;
       int it = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+      TC_CHUNK(ch)
       for (int64_t u = u_begin; u < u_end; ++it) {
         TC_SEGMENT(u)
         u += n_tiles;
@@ -276,6 +292,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         }
         umma_commit(&S.aempty[ab]);   // fires when every MMA of this item has read the A tile
       }
+      }
     }
   } else {
     // ---------------- epilogue: thread = (query row, column slice) ----------------
@@ -290,6 +307,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
     asm volatile("mov.u32 %0, %1;" : "=r"(taddr0) : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slice * SEL_SW)));
     uint32_t gt = 0;
     float r = 0.f, thr = 0.f, band = 0.f;   // per-row state of the current segment
+    for (int ch = 0; ch < n_chunks; ++ch) {
+    TC_CHUNK(ch)
     for (int64_t u = u_begin; u < u_end;) {
       TC_SEGMENT(u)
       u += n_tiles;
@@ -354,7 +373,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       constexpr int NCH = SEL_SW / 32;  // chunks per slice per tile (even)
       // per-tile bookkeeping kept to 32-bit adds: shared addresses of the barriers, the first item of this
       // slice in the tile, the number of tiles that need no tail mask
-      const int n_full = max(0, min(n_tiles, (int)(n_rows / TC_BN) - ct0));
+      const int n_full = max(0, min(n_tiles, (int)(n_rows / TC_BN) - (tile0 + ct0)));
       const bool exch = live && n_tiles >= 8;
       int32_t jb0 = (int32_t)j_begin + slice * SEL_SW;
       for (int t = 0; t < n_tiles; ++t, ++gt, jb0 += TC_BN) {
@@ -403,7 +422,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       }
       if (live) {
         // hand the surviving chunks of this (slot, slice) stream to the refine kernel
-        const int64_t stream = (int64_t)((int)blockIdx.x - tc_cta_of((int64_t)rt * T, n_units, gridDim.x)) * SEL_SLICES + slice;
+        const int64_t stream = (int64_t)ch * slots_max * SEL_SLICES +
+                               (int64_t)((int)blockIdx.x - tc_cta_of((int64_t)rt * Tch, n_units, gridDim.x)) * SEL_SLICES + slice;
         int k = 0;
         for (int e = 0; e < cnt; ++e) {
           const unsigned long long ent = list[e * TC_BM];
@@ -418,9 +438,11 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       }
       if (threadIdx.x == 64) TC_TRACE(13);
     }
+    }
   }
 
 #undef TC_SEGMENT
+#undef TC_CHUNK
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __threadfence_block();
   __syncthreads();
@@ -451,11 +473,12 @@ extern "C" int pcv_debug_tc_cta(long long *host4x256) {
 // running maxima; every recorded chunk whose approximate maximum is >= R - band is re-scored
 // item by item (lane = item) with the exact fp32 sequential-k FMA chain; winner =
 // largest exact score, ties -> lowest index.  Streams flagged -1 (too many chunks
-// inside the band, i.e. heavy exact ties) are scanned completely.
+// inside the band, i.e. heavy exact ties) are scanned completely.  A row's streams are
+// (column chunk, CTA slot, column slice): slot = position among the CTAs that touched the row tile in that chunk.
 // (256, 5): 48 registers -> 40 resident warps per SM, so M = 10240 rows finish in two waves instead of three
 __global__ void __launch_bounds__(256, 5)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
-                 int64_t M, int T, int64_t n_units, int G, float band_scale,
+                 int64_t M, int T, int Tc, int row_tiles, int slots_max, int G, float band_scale,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
                  const unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                  unsigned int *__restrict__ ovf_count_reset, int64_t *__restrict__ out_idx,
@@ -463,33 +486,47 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  // the streams of this row: (slot, slice) for the CTAs cfirst..clast that touched its row tile
   const int64_t rt = row / TC_BM;
-  const int cfirst = tc_cta_of(rt * T, n_units, G);
-  const int clast = tc_cta_of((rt + 1) * T - 1, n_units, G);
-  const int n_streams = (clast - cfirst + 1) * SEL_SLICES;
-  // every load that does not depend on another one is issued up front (one memory latency)
-  auto load_group = [&](int base, int &cnt, unsigned long long (&ents)[TC_OUT]) {
+  const int n_chunks = (T + Tc - 1) / Tc;
+  // geometry of column chunk ch for this row tile: first CTA that touched it, number of streams, first stream id
+  auto chunk_geom = [&](int ch, int &Tch, int64_t &n_units, int &cfirst, int &n_streams, int64_t &sbase) {
+    Tch = min(Tc, T - ch * Tc);
+    n_units = (int64_t)row_tiles * Tch;
+    cfirst = tc_cta_of(rt * Tch, n_units, G);
+    const int clast = tc_cta_of((rt + 1) * Tch - 1, n_units, G);
+    n_streams = (clast - cfirst + 1) * SEL_SLICES;
+    sbase = (int64_t)ch * slots_max * SEL_SLICES;
+  };
+  auto load_group = [&](int64_t sbase, int n_streams, int base, int &cnt, unsigned long long (&ents)[TC_OUT]) {
     const int s = base + lane;
     cnt = 0;
 #pragma unroll
     for (int e = 0; e < TC_OUT; ++e) ents[e] = 0ull;
     if (s < n_streams) {
-      cnt = out_cnt[(int64_t)s * M + row];
+      cnt = out_cnt[(sbase + s) * M + row];
 #pragma unroll
-      for (int e = 0; e < TC_OUT; ++e) ents[e] = out_ent[((int64_t)s * TC_OUT + e) * M + row];   // e >= cnt: stale, ignored
+      for (int e = 0; e < TC_OUT; ++e) ents[e] = out_ent[((sbase + s) * TC_OUT + e) * M + row];   // e >= cnt: stale, ignored
     }
   };
-  // issue every independent load before the first use: the first 32 streams' running maxima, their
-  // lists, the query row and the row's overflow winner all arrive in ONE memory round trip
+  // issue every independent load before the first use: the first chunk's running maxima and lists, the query
+  // row and the row's overflow winner all arrive in ONE memory round trip
+  int Tch, cfirst, n_streams;
+  int64_t n_units, sbase;
+  chunk_geom(0, Tch, n_units, cfirst, n_streams, sbase);
   int cnt;
   unsigned long long ents[TC_OUT];
-  float R = (lane < n_streams) ? out_r[(int64_t)lane * M + row] : -INFINITY;
-  load_group(0, cnt, ents);
+  float R = (lane < n_streams) ? out_r[(sbase + lane) * M + row] : -INFINITY;
+  load_group(sbase, n_streams, 0, cnt, ents);
   const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
   const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
   const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
-  for (int s = lane + 32; s < n_streams; s += 32) R = fmaxf(R, out_r[(int64_t)s * M + row]);
+  for (int s = lane + 32; s < n_streams; s += 32) R = fmaxf(R, out_r[(sbase + s) * M + row]);
+  for (int ch = 1; ch < n_chunks; ++ch) {
+    int Tx, cf, ns;
+    int64_t nu, sb;
+    chunk_geom(ch, Tx, nu, cf, ns, sb);
+    for (int s = lane; s < ns; s += 32) R = fmaxf(R, out_r[(sb + s) * M + row]);
+  }
   float q[TC_D];
   q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
   float ss = 0.f;
@@ -509,31 +546,34 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
     if (s > best || (s == best && (int32_t)j < bidx)) { best = s; bidx = (int32_t)j; }
   };
   // lane = stream while the lists are inspected, lane = item while a chunk is re-scored
-  for (int base = 0; base < n_streams; base += 32) {
-    if (base > 0) load_group(base, cnt, ents);
-    unsigned flagged = __ballot_sync(0xffffffffu, cnt < 0);
-    while (flagged) {  // exact scan of a flagged stream's whole column range
-      const int fs = base + __ffs(flagged) - 1;
-      flagged &= flagged - 1;
-      const int slot = fs / SEL_SLICES, slice = fs % SEL_SLICES;
-      const int64_t c = cfirst + slot;
-      const int64_t tb = max(tc_cta_begin(c, n_units, G), rt * T) - rt * T;
-      const int64_t te = min(tc_cta_begin(c + 1, n_units, G), (rt + 1) * T) - rt * T;
-      const int64_t j_begin = tb * TC_BN;
-      const int64_t j_end = min(n_rows, te * TC_BN);
-      for (int64_t t0 = j_begin + slice * SEL_SW; t0 < j_end; t0 += TC_BN)
-        for (int i = lane; i < SEL_SW; i += 32)
-          if (t0 + i < j_end) score(t0 + i);
-    }
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    if (ch > 0) chunk_geom(ch, Tch, n_units, cfirst, n_streams, sbase);
+    for (int base = 0; base < n_streams; base += 32) {
+      if (base > 0 || ch > 0) load_group(sbase, n_streams, base, cnt, ents);
+      unsigned flagged = __ballot_sync(0xffffffffu, cnt < 0);
+      while (flagged) {  // exact scan of a flagged stream's whole column range
+        const int fs = base + __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int slot = fs / SEL_SLICES, slice = fs % SEL_SLICES;
+        const int64_t c = cfirst + slot;
+        const int64_t tb = max(tc_cta_begin(c, n_units, G), rt * Tch) - rt * Tch;
+        const int64_t te = min(tc_cta_begin(c + 1, n_units, G), (rt + 1) * Tch) - rt * Tch;
+        const int64_t j_begin = ((int64_t)ch * Tc + tb) * TC_BN;
+        const int64_t j_end = min(n_rows, ((int64_t)ch * Tc + te) * TC_BN);
+        for (int64_t t0 = j_begin + slice * SEL_SW; t0 < j_end; t0 += TC_BN)
+          for (int i = lane; i < SEL_SW; i += 32)
+            if (t0 + i < j_end) score(t0 + i);
+      }
 #pragma unroll
-    for (int e = 0; e < TC_OUT; ++e) {
-      const bool pass = (e < cnt) && __uint_as_float((uint32_t)(ents[e] >> 32)) >= thr;
-      unsigned live = __ballot_sync(0xffffffffu, pass);
-      while (live) {
-        const int src = __ffs(live) - 1;
-        live &= live - 1;
-        const int64_t j = (int64_t)__shfl_sync(0xffffffffu, (uint32_t)ents[e], src) + lane;
-        if (j < n_rows) score(j);
+      for (int e = 0; e < TC_OUT; ++e) {
+        const bool pass = (e < cnt) && __uint_as_float((uint32_t)(ents[e] >> 32)) >= thr;
+        unsigned live = __ballot_sync(0xffffffffu, pass);
+        while (live) {
+          const int src = __ffs(live) - 1;
+          live &= live - 1;
+          const int64_t j = (int64_t)__shfl_sync(0xffffffffu, (uint32_t)ents[e], src) + lane;
+          if (j < n_rows) score(j);
+        }
       }
     }
   }
@@ -559,7 +599,8 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
 
 // ------------------------------------------------------------------ host side
 struct TcPlan {
-  int row_tiles, T, grid, slots;   // T = table tiles per row tile; slots = max CTAs touching one row tile
+  int row_tiles, T, grid, slots;   // T = table tiles per row tile; slots = max CTAs touching one row tile (per column chunk)
+  int Tc, n_chunks;                // column chunks of Tc tiles (catalogs beyond the L2: see the kernel)
   int64_t n_units;
   unsigned int ovf_cap;
   int64_t rows_per_launch;   // rows handled per kernel triple; larger M is processed in groups
@@ -567,7 +608,7 @@ struct TcPlan {
   size_t ws_bytes;           // 256 (counter) + rows_per_launch * 8 (row_best) + max var_bytes over the groups
 };
 
-constexpr size_t TC_WS_CAP = 192ull << 20;   // workspace budget: bigger problems are split into row groups
+constexpr size_t TC_WS_CAP = 1536ull << 20;  // workspace budget: bigger problems are split into row groups
 
 static void tc_plan_rows(const Table *t, int64_t M, TcPlan *p) {
   p->rows_per_launch = M;
@@ -578,15 +619,22 @@ static void tc_plan_rows(const Table *t, int64_t M, TcPlan *p) {
   if (g < 1) g = 1;
   if (g > t->sm_count) g = t->sm_count;
   p->grid = (int)g;
+  // column chunks: one chunk while the table (T tiles of 8 KB) fits comfortably in the 126 MB L2, else 32 MB chunks
+  p->Tc = (p->T <= t->tc_chunk_tiles + t->tc_chunk_tiles / 2) ? p->T : t->tc_chunk_tiles;
+  p->n_chunks = (p->T + p->Tc - 1) / p->Tc;
   int slots = 1;
-  for (int64_t rt = 0; rt < p->row_tiles; ++rt) {
-    const int n = tc_cta_of((rt + 1) * p->T - 1, p->n_units, p->grid) - tc_cta_of(rt * p->T, p->n_units, p->grid) + 1;
-    if (n > slots) slots = n;
+  for (int ch = 0; ch < p->n_chunks; ch += (p->n_chunks > 1 ? p->n_chunks - 1 : 1)) {   // the full-size and the last chunk
+    const int Tch = (p->T - ch * p->Tc < p->Tc) ? (p->T - ch * p->Tc) : p->Tc;
+    const int64_t nu = (int64_t)p->row_tiles * Tch;
+    for (int64_t rt = 0; rt < p->row_tiles; ++rt) {
+      const int n = tc_cta_of((rt + 1) * Tch - 1, nu, p->grid) - tc_cta_of(rt * Tch, nu, p->grid) + 1;
+      if (n > slots) slots = n;
+    }
   }
   p->slots = slots;
   // per (stream, row): running max (4) + count (4) + TC_OUT recorded chunks (8 each);
   // per row: packed overflow winner (8); overflow list: ovf_cap x (8 + 4), split evenly over the CTAs
-  const size_t n_sr = (size_t)SEL_SLICES * p->slots * (size_t)M;
+  const size_t n_sr = (size_t)SEL_SLICES * p->slots * p->n_chunks * (size_t)M;
   p->ovf_cap = (unsigned int)(n_sr / 16 < 65536 ? 65536 : (n_sr / 16 > (1u << 24) ? (1u << 24) : n_sr / 16));
   p->var_bytes = n_sr * (8 + 8 * TC_OUT) + (size_t)p->ovf_cap * 12;
   p->ws_bytes = 256 + (size_t)M * 8 + p->var_bytes;
@@ -628,6 +676,11 @@ __global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, f
 int table_init_tc(Table *t) {
   t->tmap_valid = 0;
   t->packed = nullptr;
+  t->tc_chunk_tiles = 4096;     // 4096 tiles x 8 KB = 32 MB of the pre-swizzled table per column chunk
+  if (const char *e = getenv("PCV_TC_CHUNK_TILES")) {   // test hook: force chunking on small catalogs
+    const int v = atoi(e);
+    if (v >= 1) t->tc_chunk_tiles = v;
+  }
   if (t->dim != TC_D) return PCV_OK;
   float *p = nullptr;
   cudaError_t e = cudaMalloc(&p, (size_t)t->n_rows * TC_D * sizeof(float));
@@ -689,18 +742,18 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     // (see pcv_score_select_workspace_bytes) and tc_refine_kernel re-zeroes what a call dirtied
     TcPlan g;   // the last group may be shorter: its own partition
     tc_plan_rows(t, m, &g);
-    const size_t n_sr = (size_t)SEL_SLICES * g.slots * (size_t)m;       // (stream, row) pairs of this group
+    const size_t n_sr = (size_t)SEL_SLICES * g.slots * g.n_chunks * (size_t)m;   // (stream, row) pairs of this group
     unsigned long long *ent = var;                                     // [n_sr][TC_OUT]
     unsigned long long *ovf_ent = ent + n_sr * TC_OUT;                 // [ovf_cap]
     float *rr = reinterpret_cast<float *>(ovf_ent + g.ovf_cap);        // [n_sr]
     int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);              // [n_sr]
     int32_t *ovf_row = cc + n_sr;                                      // [ovf_cap]
-    score_select_tc_kernel<<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.n_units,
-                                                                       band_scale, rr, cc, ent, row_best, ovf_ent,
+    score_select_tc_kernel<<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.Tc, g.row_tiles,
+                                                                       g.slots, band_scale, rr, cc, ent, row_best, ovf_ent,
                                                                        ovf_row, g.ovf_cap / (unsigned)g.grid);
     PCV_LAUNCH_CHECK();
-    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.n_units, g.grid,
-                                                             band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
+    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.Tc, g.row_tiles,
+                                                             g.slots, g.grid, band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
                                                              out_val ? out_val + r0 : nullptr);
     if (cudaPeekAtLastError() != cudaSuccess) {
       // the filter ran but the kernel that re-zeroes the head did not launch: heal the workspace here, so that a

@@ -45,14 +45,19 @@ class BaseCVAE(nn.Module):
                              "(every reference subclass hard-codes fine_tune=False)")
         self.noise = NoiseSource()
         self.select_engine = "auto"
+        # sampled pivots without caller-supplied noise: "rejection" = exact O(1)-per-row sampler (csrc/sampler.cu),
+        # "race" = the exponential race over the whole catalog with in-kernel Philox noise (O(N) per row)
+        self.pivot_sampler = "rejection"
         self.ce_engine = "exact"   # "tf32": full-catalog CE logits on the tensor cores (reduced-precision tolerance)
         self._table = None
+        self._full = None    # full-catalog handle while vocab-parallel (the sampler draws over every row)
         self._vp = None      # vocab-parallel state: (group, lo, hi) once enable_vocab_parallel() is called
 
     # ---- extension state is rebuilt lazily (whole-model pickling, train_generative.py:199)
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_table"] = None
+        st["_full"] = None
         st["_vp"] = None
         st.pop("_head_cache", None)
         return st
@@ -80,7 +85,20 @@ class BaseCVAE(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._table = None
+        self._full = None
         return super()._apply(fn, *a, **k)
+
+    def full_table(self):
+        """Handle over the WHOLE catalog (== item_table() unless vocab-parallel)."""
+        if self._vp is None:
+            return self.item_table()
+        w = self.docEmbed.weight
+        t = getattr(self, "_full", None)
+        if t is None or t.weight.data_ptr() != w.data_ptr() or t.n_rows != w.shape[0] or t.version != w._version:
+            t = ops.Table(w.detach())
+            t.version = w._version
+            self._full = t
+        return t
 
     def item_table(self):
         w = self.docEmbed.weight

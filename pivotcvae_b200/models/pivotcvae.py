@@ -66,6 +66,11 @@ class UserPivotCVAE(BaseCVAE):
             if self._vp is not None:      # external noise is [B, N]: every shard reads its own columns
                 noise = noise[:, self._vp[1]:self._vp[2]].contiguous()
             return self._select(q, "exprace", noise=noise)
+        if self.pivot_sampler == "rejection":
+            # throughput mode: the same Categorical(sigmoid(scores)) drawn exactly in O(1) per row (csrc/sampler.cu);
+            # needs the whole catalog, which every vocab-parallel rank keeps anyway -> no collective
+            from .. import ops
+            return ops.sigmoid_categorical(self.full_table(), q, **self.noise.stream_args(q.shape[0]))
         return self._select(q, "exprace", **self.noise.stream_args(q.shape[0]))
 
     def pick_pivot(self, pivot_output, true_pivot=[]):

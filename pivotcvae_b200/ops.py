@@ -192,6 +192,20 @@ def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="
     return idx, val
 
 
+def sigmoid_categorical(table, Q, seed=0, offset=0, offset_dev=None, want_iters=False):
+    """idx[i] ~ Categorical(sigmoid(Q[i] . W^T)) over the whole catalog, exact rejection sampler (csrc/sampler.cu)."""
+    Q = _f32(Q, "Q")
+    M, D = Q.shape
+    if D != table.dim:
+        raise L.PcvError("Q has dim %d, table has dim %d" % (D, table.dim))
+    idx = torch.empty(M, dtype=torch.int64, device=Q.device)
+    iters = torch.empty(M, dtype=torch.int32, device=Q.device) if want_iters else None
+    with torch.cuda.device(Q.device), _timed("sigmoid_categorical_M%d" % M):
+        L.check(L.load().pcv_sigmoid_categorical(table.handle, _ptr(Q), M, int(seed), int(offset), _ptr(offset_dev),
+                                                 _ptr(idx), _ptr(iters), _stream()), "pcv_sigmoid_categorical")
+    return (idx, iters) if want_iters else idx
+
+
 def score_logits(table, Q):
     Q = _f32(Q, "Q")
     out = torch.empty(Q.shape[0], table.n_rows, dtype=torch.float32, device=Q.device)

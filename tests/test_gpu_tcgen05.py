@@ -140,3 +140,28 @@ def test_tc_row_groups_and_max_size(ops):
     assert bool(((exact - val).abs() <= 1e-5).all())
     si, sv = ops.score_select(tab, Q[:512], "greedy", engine="simt")
     assert torch.equal(si, idx[:512]) and torch.equal(sv, val[:512])
+
+
+@pytest.mark.parametrize("n_items,M,chunk_tiles", [(50000, 700, 16), (100003, 515, 64), (9000, 300, 3), (65536, 1500, 100)])
+def test_tc_column_chunks(ops, monkeypatch, n_items, M, chunk_tiles):
+    """Catalogs beyond the L2 are walked in column chunks (32 MB each in production); PCV_TC_CHUNK_TILES forces the
+    chunked partition on small catalogs: same bits as the oracle, ties across chunks -> lowest index, heavy ties
+    (flagged streams, overflow lists) inside a chunk."""
+    monkeypatch.setenv("PCV_TC_CHUNK_TILES", str(chunk_tiles))
+    rng = np.random.default_rng(n_items + chunk_tiles)
+    W = _unit(rng, n_items)
+    Q = (rng.standard_normal((M, 8)) * rng.uniform(0.05, 3.0, (M, 1))).astype(np.float32)
+    W[n_items - 1] = W[5]                       # duplicates in the first, a middle and the last chunk
+    W[n_items // 2 + 3] = W[5]
+    W[chunk_tiles * 256 + 7] = W[5]
+    Q[0] = 1.7 * W[5]
+    W[n_items // 3: n_items // 3 + 700] = W[n_items // 3]      # 700-way tie block inside one chunk
+    Q[1] = 2.0 * W[n_items // 3]
+    tab = ops.Table(T(W))
+    idx, val = ops.score_select(tab, T(Q), "greedy", engine="tcgen05")
+    oi, ov = oracle.score_select(W, Q)
+    assert np.array_equal(N(idx), oi) and np.array_equal(N(val), ov)
+    assert N(idx)[0] == 5 and N(idx)[1] == n_items // 3
+    monkeypatch.delenv("PCV_TC_CHUNK_TILES")
+    idx1, val1 = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine="tcgen05")     # one chunk: same answer
+    assert torch.equal(idx, idx1) and torch.equal(val, val1)
