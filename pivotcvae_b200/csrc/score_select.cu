@@ -411,7 +411,7 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
                  ? PCV_ENGINE_TCGEN05 : PCV_ENGINE_SIMT;
   if (engine == PCV_ENGINE_TCGEN05) {
     if (opts->mode != PCV_SELECT_GREEDY || !score_select_tc_supported(t)) {
-      set_error("score_select: tcgen05 engine needs greedy mode and dim 8 (dim %d, mode %d)", t->dim, opts->mode);
+      set_error("score_select: tcgen05 engine needs greedy mode and dim 8, 16, 32, 64 or 128 (dim %d, mode %d)", t->dim, opts->mode);
       return PCV_ERR_UNSUPPORTED;
     }
     return score_select_tc(t, Q, M, out_idx, out_val, workspace, workspace_bytes, st);

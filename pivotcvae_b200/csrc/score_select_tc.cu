@@ -57,19 +57,60 @@ constexpr int SEL_EPI_WARPS = 16;                     // multiple of 4 (a warp r
 constexpr int SEL_SLICES = SEL_EPI_WARPS / 4;         // column slices of a tile
 constexpr int SEL_SW = TC_BN / SEL_SLICES;            // columns per slice
 constexpr int SEL_THREADS = 64 + 32 * SEL_EPI_WARPS;  // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
-constexpr int SEL_STAGES = 12;                        // 8 KB table tiles in flight
-constexpr int TC_CAP = 16;                            // in-kernel recorded-chunk list capacity per (slice, row)
 constexpr int TC_OUT = 4;                            // recorded chunks handed to the refine kernel per (stream, row)
 
+// The embedding dimension D = 8 * KA is walked in K-ATOMS of 8 fp32 (= 32 bytes = one kind::tf32 k-step).  Operand
+// tiles are stored k-atom-major, each atom a [rows][32 B] SWIZZLE_32B image, so the D = 8 layout (KA = 1) is
+// the special case and a larger D only adds MMAs (accumulating in TMEM) per table tile, not a new layout:
+//   table tile j: packed[(j * KA + a) * 2048 floats ..]  = atom a of rows 256 j .. 256 j + 255
+//   ring stage  : KS consecutive atoms of one tile (one TMA bulk copy of KS * 8 KB)
+template <int KA>
+struct TcCfg {
+  static constexpr int D = 8 * KA;
+  static constexpr int KS = KA == 1 ? 1 : 2;          // k-atoms per ring stage
+  static constexpr int STAGES = KA == 1 ? 12 : 6;     // 96 KB of table tiles in flight
+  static constexpr int A_BUFS = KA <= 8 ? 2 : 1;      // query tiles: double-buffered across segments while they fit
+  static constexpr int CAP = KA <= 4 ? 16 : 8;        // in-kernel recorded-chunk list capacity per (slice, row)
+  static constexpr int ATOM_A = TC_BM * 8;            // floats per k-atom of the query tile
+  static constexpr int ATOM_B = TC_BN * 8;            // floats per k-atom of a table tile
+  static constexpr uint32_t STAGE_BYTES = KS * ATOM_B * 4;
+};
+
+template <int KA>
 struct __align__(1024) TcSmem {
-  float b[SEL_STAGES][TC_BN * TC_D];            // SWIZZLE_32B tiles written by TMA
-  float a[2][TC_BM * TC_D];                    // query tiles (double-buffered across work items), same layout
-  unsigned long long cand[SEL_SLICES][TC_CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
+  using C = TcCfg<KA>;
+  float b[C::STAGES][C::KS * C::ATOM_B];       // SWIZZLE_32B tile atoms written by TMA
+  float a[C::A_BUFS][KA * C::ATOM_A];          // query tiles, same layout
+  unsigned long long cand[SEL_SLICES][C::CAP][TC_BM];  // recorded 32-item chunks per (slice, row): (approx max bits << 32) | first item
   float rmax[TC_BM];                           // running max per row, shared by the column slices
-  unsigned long long full[SEL_STAGES], empty[SEL_STAGES], tfull[2], tempty[2], afull[2], aempty[2];
+  unsigned long long full[C::STAGES], empty[C::STAGES], tfull[2], tempty[2], afull[2], aempty[2];
   uint32_t tmem_base;
   unsigned int ovf_n;                           // overflow entries this CTA has spilled to its region of the global list
 };
+
+// exact fp32 sequential-k FMA chain of one item against a query row held in global memory
+template <int D>
+__device__ __forceinline__ float tc_exact_score(const float *__restrict__ q, const float *__restrict__ w) {
+  float sc = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; k += 4) {
+    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(q + k));
+    const float4 w4 = __ldg(reinterpret_cast<const float4 *>(w + k));
+    sc = fmaf(q4.x, w4.x, sc); sc = fmaf(q4.y, w4.y, sc); sc = fmaf(q4.z, w4.z, sc); sc = fmaf(q4.w, w4.w, sc);
+  }
+  return sc;
+}
+// |q|^2 with the same left-to-right FMA chain everywhere it is needed (filter and refine must agree on the band)
+template <int D>
+__device__ __forceinline__ float tc_norm2(const float *__restrict__ q) {
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; k += 4) {
+    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(q + k));
+    ss = fmaf(q4.x, q4.x, ss); ss = fmaf(q4.y, q4.y, ss); ss = fmaf(q4.z, q4.z, ss); ss = fmaf(q4.w, q4.w, ss);
+  }
+  return ss;
+}
 
 // max of 32 accumulator values; g[0..10] are the maxima of the 3-element groups
 // (g[10] covers elements 30, 31) so the rare slow path can skip whole groups.
@@ -111,6 +152,7 @@ __device__ __noinline__ bool tc_spill(unsigned int *ovf_n, unsigned long long *_
 
 // One warp per spilled chunk (lane = item): exact fp32 re-score, the winner is merged into row_best[row],
 // which tc_refine_kernel folds into the row's result.
+template <int D>
 __device__ __noinline__ void tc_rescore_overflow(const float *__restrict__ W, int64_t n_rows, const float *__restrict__ Q,
                                                  const unsigned long long *__restrict__ ent, const int32_t *__restrict__ rows,
                                                  unsigned int n, unsigned long long *__restrict__ row_best) {
@@ -121,14 +163,7 @@ __device__ __noinline__ void tc_rescore_overflow(const float *__restrict__ W, in
     float best = -INFINITY;
     int32_t bidx = 0x7fffffff;
     if (j < n_rows) {
-      const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-      const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
-      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
-      float sc = 0.f;
-      sc = fmaf(q0.x, w0.x, sc); sc = fmaf(q0.y, w0.y, sc); sc = fmaf(q0.z, w0.z, sc); sc = fmaf(q0.w, w0.w, sc);
-      sc = fmaf(q1.x, w1.x, sc); sc = fmaf(q1.y, w1.y, sc); sc = fmaf(q1.z, w1.z, sc); sc = fmaf(q1.w, w1.w, sc);
-      best = sc;
+      best = tc_exact_score<D>(Q + row * D, W + j * D);
       bidx = (int32_t)j;
     }
 #pragma unroll
@@ -158,21 +193,24 @@ __host__ __device__ __forceinline__ int tc_cta_of(int64_t x, int64_t n_units, in
 //             then lane 0 streams that item's table tiles with TMA bulk copies;
 //   warp 1  : lane 0 issues one tcgen05.mma per tile (TMEM alloc/dealloc by the whole warp);
 //   warps 2+: epilogue (thread = query row x column slice).
+template <int KA>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
                        const float *__restrict__ Q, int64_t M, int T, int Tc, int row_tiles, int slots_max,
                        float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
                        unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                        unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cta_cap) {
+  using C = TcCfg<KA>;
+  constexpr int D = C::D;
   extern __shared__ unsigned char smem_raw[];
-  TcSmem &S = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  TcSmem<KA> &S = *reinterpret_cast<TcSmem<KA> *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_TRACE(0);
 
   if (threadIdx.x == 0) {
     S.ovf_n = 0u;
-    for (int s = 0; s < SEL_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.tfull[b], 1); mbar_init(&S.tempty[b], SEL_EPI_WARPS);
       mbar_init(&S.afull[b], 1); mbar_init(&S.aempty[b], 1);
@@ -210,7 +248,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
 
   if (warp == 0) {
     // ---------------- producer: A tile of the item, then its table tiles ----------------
-    uint32_t gt = 0;   // tiles issued so far (ring position)
+    uint32_t gs = 0;   // ring stages issued so far (KA / KS per table tile)
     int it = 0;        // items started so far
     for (int ch = 0; ch < n_chunks; ++ch) {
     TC_CHUNK(ch)
@@ -218,24 +256,27 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       TC_SEGMENT(u)
       u += n_tiles;
       (void)j_end;
-      const int ab = it & 1;
-      mbar_wait(&S.aempty[ab], ((it >> 1) & 1) ^ 1);   // MMAs of the segment that used this A buffer are done
+      const int ab = it % C::A_BUFS;
+      mbar_wait(&S.aempty[ab], ((it / C::A_BUFS) & 1) ^ 1);   // MMAs of the segment that used this A buffer are done
       {
-        // 128 query rows: row t at byte t*32, 16-byte chunk c at ((c ^ bit2(t)) * 16)  (SWIZZLE_32B image)
+        // 128 query rows per k-atom: row t at byte t*32, 16-byte chunk c at ((c ^ bit2(t)) * 16)  (SWIZZLE_32B image)
         const int64_t row_base = (int64_t)rt * TC_BM;
 #pragma unroll
         for (int i = 0; i < TC_BM / 32; ++i) {
           const int t = lane + 32 * i;
           const int64_t row = row_base + t;
-          float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-          if (row < M) {
-            q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-            q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-          }
           const int sw = (t >> 2) & 1;
-          float4 *dst = reinterpret_cast<float4 *>(S.a[ab] + t * TC_D);
-          dst[0 ^ sw] = q0;
-          dst[1 ^ sw] = q1;
+#pragma unroll 4
+          for (int a = 0; a < KA; ++a) {
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+            if (row < M) {
+              q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * D + a * 8));
+              q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * D + a * 8) + 1);
+            }
+            float4 *dst = reinterpret_cast<float4 *>(S.a[ab] + a * C::ATOM_A + t * 8);
+            dst[0 ^ sw] = q0;
+            dst[1 ^ sw] = q1;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -243,15 +284,20 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         if (lane == 0 && it == 0) TC_TRACE(2);
       }
       if (lane == 0) {
-        for (int t = 0; t < n_tiles; ++t, ++gt) {
-          const int s = gt % SEL_STAGES;
-          const uint32_t ph = (gt / SEL_STAGES) & 1;
-          mbar_wait(&S.empty[s], ph ^ 1);
+        for (int t = 0; t < n_tiles; ++t) {
           const int64_t j0 = j_begin + (int64_t)t * TC_BN;
-          const uint32_t bytes = (uint32_t)min((int64_t)TC_TILE_BYTES, (n_rows - j0) * (int64_t)(TC_D * 4));
-          mbar_expect_tx(&S.full[s], bytes);  // rows past the end of the table keep stale data: masked below
-          tma_bulk_load(S.b[s], Wsw + j0 * TC_D, bytes, &S.full[s]);
-          if (gt == 0) TC_TRACE(3);
+#pragma unroll 1
+          for (int kg = 0; kg < KA / C::KS; ++kg, ++gs) {
+            const int s = gs % C::STAGES;
+            const uint32_t ph = (gs / C::STAGES) & 1;
+            mbar_wait(&S.empty[s], ph ^ 1);
+            // D = 8: the packed copy is exactly n_rows x 32 B, the last tile is short (rows past the end of the
+            // table keep stale data: masked in the epilogue); D > 8: the copy is padded to whole tiles
+            const uint32_t bytes = KA == 1 ? (uint32_t)min((int64_t)C::STAGE_BYTES, (n_rows - j0) * (int64_t)32) : C::STAGE_BYTES;
+            mbar_expect_tx(&S.full[s], bytes);
+            tma_bulk_load(S.b[s], Wsw + j0 * D + (int64_t)kg * (C::KS * C::ATOM_B), bytes, &S.full[s]);
+            if (gs == 0) TC_TRACE(3);
+          }
         }
       }
       __syncwarp();
@@ -260,7 +306,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      uint32_t gt = 0;
+      uint32_t gt = 0, gs = 0;
       int it = 0;
       for (int ch = 0; ch < n_chunks; ++ch) {
       TC_CHUNK(ch)
@@ -268,26 +314,33 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         TC_SEGMENT(u)
         u += n_tiles;
         (void)j_begin; (void)j_end;
-        const int ab = it & 1;
-        mbar_wait(&S.afull[ab], (it >> 1) & 1);
+        const int ab = it % C::A_BUFS;
+        mbar_wait(&S.afull[ab], (it / C::A_BUFS) & 1);
         const uint64_t adesc = umma_desc_sw32(S.a[ab]);
         for (int t = 0; t < n_tiles; ++t, ++gt) {
-          const int s = gt % SEL_STAGES;
-          const uint32_t ph = (gt / SEL_STAGES) & 1;
           const int buf = gt & 1;
           const uint32_t bph = (gt >> 1) & 1;
           mbar_wait(&S.tempty[buf], bph ^ 1);
 #ifdef PCV_TC_TRACE
           if (blockIdx.x == 0 && gt >= 40 && gt < 44) g_tc_mma[2 * (gt - 40)] = clock64();
 #endif
-          mbar_wait(&S.full[s], ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+          for (int kg = 0; kg < KA / C::KS; ++kg, ++gs) {
+            const int s = gs % C::STAGES;
+            const uint32_t ph = (gs / C::STAGES) & 1;
+            mbar_wait(&S.full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef PCV_TC_TRACE
-          if (blockIdx.x == 0 && gt >= 40 && gt < 44) g_tc_mma[2 * (gt - 40) + 1] = clock64();
+            if (blockIdx.x == 0 && gt >= 40 && gt < 44) g_tc_mma[2 * (gt - 40) + 1] = clock64();
 #endif
-          if (gt == 0) TC_TRACE(4);
-          umma_tf32(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC, 0);
-          umma_commit(&S.empty[s]);
+            if (gt == 0) TC_TRACE(4);
+            // one k-step (8 fp32 = 32 B) per k-atom: the descriptors step by whole atoms (4 KB of A, 8 KB of B)
+#pragma unroll
+            for (int a = 0; a < C::KS; ++a)
+              umma_tf32(tmem + buf * TC_BN, adesc + (uint64_t)(((kg * C::KS + a) * C::ATOM_A * 4) >> 4),
+                        umma_desc_sw32(S.b[s] + a * C::ATOM_B), TC_IDESC, (kg | a) != 0);
+            umma_commit(&S.empty[s]);
+          }
           umma_commit(&S.tfull[buf]);
         }
         umma_commit(&S.aempty[ab]);   // fires when every MMA of this item has read the A tile
@@ -316,12 +369,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       const bool live = row < M;
       {   // every segment starts on new rows: reset the running max
         float ss = 0.f;
-        if (live) {
-          const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-          const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
-          ss = fmaf(q0.x, q0.x, ss); ss = fmaf(q0.y, q0.y, ss); ss = fmaf(q0.z, q0.z, ss); ss = fmaf(q0.w, q0.w, ss);
-          ss = fmaf(q1.x, q1.x, ss); ss = fmaf(q1.y, q1.y, ss); ss = fmaf(q1.z, q1.z, ss); ss = fmaf(q1.w, q1.w, ss);
-        }
+        if (live) ss = tc_norm2<D>(Q + row * D);
         band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
         // running max of the approximate scores; finite start so that masked (-inf) columns
         // never pass, +inf for dummy rows so that nothing ever passes
@@ -355,8 +403,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         if (m >= thr) {
           r = fmaxf(r, m);
           thr = r - band;
-          if (cnt == TC_CAP) compact();
-          if (cnt < TC_CAP) {
+          if (cnt == C::CAP) compact();
+          if (cnt < C::CAP) {
             list[cnt * TC_BM] = ((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb;
             ++cnt;
           } else {
@@ -454,7 +502,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
   // Exact re-score of the chunks this CTA spilled (normally none); kept out of line so that the hot loop's
   // code layout does not depend on it
   const unsigned int n_ovf = min(S.ovf_n, ovf_cta_cap);
-  if (n_ovf) tc_rescore_overflow(W, n_rows, Q, ovf_ent + (size_t)blockIdx.x * ovf_cta_cap, ovf_row + (size_t)blockIdx.x * ovf_cta_cap, n_ovf, row_best);
+  if (n_ovf) tc_rescore_overflow<D>(W, n_rows, Q, ovf_ent + (size_t)blockIdx.x * ovf_cta_cap, ovf_row + (size_t)blockIdx.x * ovf_cta_cap, n_ovf, row_best);
 }
 
 #ifdef PCV_TC_TRACE
@@ -476,7 +524,8 @@ extern "C" int pcv_debug_tc_cta(long long *host4x256) {
 // inside the band, i.e. heavy exact ties) are scanned completely.  A row's streams are
 // (column chunk, CTA slot, column slice): slot = position among the CTAs that touched the row tile in that chunk.
 // (256, 5): 48 registers -> 40 resident warps per SM, so M = 10240 rows finish in two waves instead of three
-__global__ void __launch_bounds__(256, 5)
+template <int D>
+__global__ void __launch_bounds__(256, D <= 16 ? 5 : 4)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
                  int64_t M, int T, int Tc, int row_tiles, int slots_max, int G, float band_scale,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
@@ -517,8 +566,8 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   unsigned long long ents[TC_OUT];
   float R = (lane < n_streams) ? out_r[(sbase + lane) * M + row] : -INFINITY;
   load_group(sbase, n_streams, 0, cnt, ents);
-  const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D));
-  const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * TC_D) + 1);
+  const float4 q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * D));
+  const float4 q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * D) + 1);
   const unsigned long long pb = row_best[row];   // exact winner among the overflow chunks (0 = none)
   for (int s = lane + 32; s < n_streams; s += 32) R = fmaxf(R, out_r[(sbase + s) * M + row]);
   for (int ch = 1; ch < n_chunks; ++ch) {
@@ -527,22 +576,30 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
     chunk_geom(ch, Tx, nu, cf, ns, sb);
     for (int s = lane; s < ns; s += 32) R = fmaxf(R, out_r[(sb + s) * M + row]);
   }
-  float q[TC_D];
+  float q[8];   // D = 8: the whole query row lives in registers; larger D re-reads it (L1 broadcast) per re-scored item
   q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
   float ss = 0.f;
+  if constexpr (D == 8) {
 #pragma unroll
-  for (int k = 0; k < TC_D; ++k) ss = fmaf(q[k], q[k], ss);
+    for (int k = 0; k < 8; ++k) ss = fmaf(q[k], q[k], ss);
+  } else {
+    ss = tc_norm2<D>(Q + row * D);
+  }
   const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
   R = warp_max(R);
   const float thr = R - band;
   float best = -INFINITY;
   int32_t bidx = 0x7fffffff;
   auto score = [&](int64_t j) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D));
-    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * TC_D) + 1);
     float s = 0.f;
-    s = fmaf(q[0], w0.x, s); s = fmaf(q[1], w0.y, s); s = fmaf(q[2], w0.z, s); s = fmaf(q[3], w0.w, s);
-    s = fmaf(q[4], w1.x, s); s = fmaf(q[5], w1.y, s); s = fmaf(q[6], w1.z, s); s = fmaf(q[7], w1.w, s);
+    if constexpr (D == 8) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4 *>(W + j * D));
+      const float4 w1 = __ldg(reinterpret_cast<const float4 *>(W + j * D) + 1);
+      s = fmaf(q[0], w0.x, s); s = fmaf(q[1], w0.y, s); s = fmaf(q[2], w0.z, s); s = fmaf(q[3], w0.w, s);
+      s = fmaf(q[4], w1.x, s); s = fmaf(q[5], w1.y, s); s = fmaf(q[6], w1.z, s); s = fmaf(q[7], w1.w, s);
+    } else {
+      s = tc_exact_score<D>(Q + row * D, W + j * D);
+    }
     if (s > best || (s == best && (int32_t)j < bidx)) { best = s; bidx = (int32_t)j; }
   };
   // lane = stream while the lists are inspected, lane = item while a chunk is re-scored
@@ -654,23 +711,26 @@ static void tc_plan(const Table *t, int64_t M, TcPlan *p) {
   }
 }
 
-bool score_select_tc_supported(const Table *t) { return t->dim == TC_D && t->tmap_valid; }
+static bool tc_dim_ok(int dim) { return dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128; }
+bool score_select_tc_supported(const Table *t) { return tc_dim_ok(t->dim) && t->tmap_valid; }
 
 size_t score_select_tc_workspace(const Table *t, int64_t M) {
-  if (t->dim != TC_D) return 0;
+  if (!tc_dim_ok(t->dim)) return 0;
   TcPlan p;
   tc_plan(t, M, &p);
   return p.ws_bytes;
 }
 
-// Pre-swizzled image of the table: row j keeps its 32 bytes, with the two 16-byte chunks
-// swapped when bit 2 of j is set (Swizzle<1,4,3>: address bit 4 ^= bit 7).
-__global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, float4 *__restrict__ out) {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
-  if (f >= n_rows * 2) return;
-  const int64_t j = f >> 1;
+// Pre-swizzled image of the table.  Per 256-row tile and k-atom a (8 consecutive fp32 of a row) a [256][32 B] block in
+// which the two 16-byte chunks of a row are swapped when bit 2 of the row index is set (Swizzle<1,4,3>: address bit 4 ^=
+// bit 7); the ka atoms of a tile follow each other.  D = 8 (ka = 1): row j simply keeps its 32 bytes, chunks swapped.
+__global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, int ka, float4 *__restrict__ out) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index of W
+  if (f >= n_rows * 2 * ka) return;
+  const int64_t j = f / (2 * ka);
+  const int a = (int)(f % (2 * ka)) >> 1;
   const int c = (int)(f & 1);
-  out[j * 2 + (c ^ (int)((j >> 2) & 1))] = W[f];
+  out[((j >> 8) * ka + a) * (TC_BN * 2) + (j & (TC_BN - 1)) * 2 + (c ^ (int)((j >> 2) & 1))] = W[f];
 }
 
 int table_init_tc(Table *t) {
@@ -681,17 +741,22 @@ int table_init_tc(Table *t) {
     const int v = atoi(e);
     if (v >= 1) t->tc_chunk_tiles = v;
   }
-  if (t->dim != TC_D) return PCV_OK;
+  if (!tc_dim_ok(t->dim)) return PCV_OK;
+  const int ka = t->dim / 8;
+  // D = 8: exactly n_rows x 32 B (the last tile is copied short); D > 8: whole tiles, zero-padded
+  const int64_t rows_alloc = ka == 1 ? t->n_rows : (t->n_rows + TC_BN - 1) / TC_BN * TC_BN;
+  const size_t packed_bytes = (size_t)rows_alloc * t->dim * sizeof(float);
   float *p = nullptr;
-  cudaError_t e = cudaMalloc(&p, (size_t)t->n_rows * TC_D * sizeof(float));
+  cudaError_t e = cudaMalloc(&p, packed_bytes);
   if (e != cudaSuccess) {   // no silent downgrade to the 8x slower SIMT engine: the caller sees the failure
     cudaGetLastError();
-    set_error("pcv_table_create: cudaMalloc of the pre-swizzled table copy (%zu bytes) -> %s",
-              (size_t)t->n_rows * TC_D * sizeof(float), cudaGetErrorString(e));
+    set_error("pcv_table_create: cudaMalloc of the pre-swizzled table copy (%zu bytes) -> %s", packed_bytes,
+              cudaGetErrorString(e));
     return PCV_ERR_CUDA;
   }
-  const int64_t chunks = t->n_rows * 2;
-  pack_sw32_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(reinterpret_cast<const float4 *>(t->W), t->n_rows,
+  if (ka > 1) cudaMemset(p, 0, packed_bytes);
+  const int64_t chunks = t->n_rows * 2 * ka;
+  pack_sw32_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(reinterpret_cast<const float4 *>(t->W), t->n_rows, ka,
                                                               reinterpret_cast<float4 *>(p));
   count_launch();
   e = cudaDeviceSynchronize();
@@ -714,8 +779,10 @@ void table_free_tc(Table *t) {
 void launch_select_finalize(const float *pv, const int32_t *pi, int n_parts, int64_t M, int64_t row_offset,
                             int64_t *out_idx, float *out_val, cudaStream_t st);
 
-int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val, void *ws,
-                    size_t ws_bytes, cudaStream_t st) {
+template <int KA>
+static int score_select_tc_impl(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val, void *ws,
+                                size_t ws_bytes, cudaStream_t st) {
+  constexpr int D = 8 * KA;
   TcPlan p;
   tc_plan(t, M, &p);
   if (ws == nullptr || ws_bytes < p.ws_bytes) {
@@ -727,17 +794,17 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
   unsigned int *ovf_count = reinterpret_cast<unsigned int *>(ws);
   unsigned long long *row_best = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);   // [Mg]
   unsigned long long *var = row_best + Mg;                             // per-group layout below
-  const size_t smem = sizeof(TcSmem) + 1024;
+  const size_t smem = sizeof(TcSmem<KA>) + 1024;
   static bool attr_set[64] = {false};
   if (!attr_set[t->device & 63]) {
-    PCV_CUDA(cudaFuncSetAttribute(score_select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCV_CUDA(cudaFuncSetAttribute(score_select_tc_kernel<KA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[t->device & 63] = true;
   }
   // |tf32 chain - fp32 chain| <= 1.25 * 2^-9 * |q| * max|w|; the band is twice that
   const float band_scale = 2.0f * 1.25f * 0.001953125f * t->max_row_norm;
   for (int64_t r0 = 0; r0 < M; r0 += Mg) {   // row groups reuse the workspace back to back on the stream
     const int64_t m = (M - r0 < Mg) ? (M - r0) : Mg;
-    const float *Qg = Q + r0 * TC_D;
+    const float *Qg = Q + r0 * D;
     // row_best / ovf_count are zero on entry: the workspace must be zero-initialised ONCE by the caller
     // (see pcv_score_select_workspace_bytes) and tc_refine_kernel re-zeroes what a call dirtied
     TcPlan g;   // the last group may be shorter: its own partition
@@ -748,11 +815,11 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     float *rr = reinterpret_cast<float *>(ovf_ent + g.ovf_cap);        // [n_sr]
     int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);              // [n_sr]
     int32_t *ovf_row = cc + n_sr;                                      // [ovf_cap]
-    score_select_tc_kernel<<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.Tc, g.row_tiles,
+    score_select_tc_kernel<KA><<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.Tc, g.row_tiles,
                                                                        g.slots, band_scale, rr, cc, ent, row_best, ovf_ent,
                                                                        ovf_row, g.ovf_cap / (unsigned)g.grid);
     PCV_LAUNCH_CHECK();
-    tc_refine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.Tc, g.row_tiles,
+    tc_refine_kernel<D><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.Tc, g.row_tiles,
                                                              g.slots, g.grid, band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
                                                              out_val ? out_val + r0 : nullptr);
     if (cudaPeekAtLastError() != cudaSuccess) {
@@ -766,6 +833,19 @@ int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx,
     count_launch();
   }
   return PCV_OK;
+}
+
+int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val, void *ws,
+                    size_t ws_bytes, cudaStream_t st) {
+  switch (t->dim) {
+    case 8: return score_select_tc_impl<1>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+    case 16: return score_select_tc_impl<2>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+    case 32: return score_select_tc_impl<4>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+    case 64: return score_select_tc_impl<8>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+    case 128: return score_select_tc_impl<16>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+  }
+  set_error("score_select(tcgen05): dim %d unsupported (8, 16, 32, 64 or 128)", t->dim);
+  return PCV_ERR_UNSUPPORTED;
 }
 
 }  // namespace pcv

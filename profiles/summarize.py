@@ -43,14 +43,35 @@ def launches(path):
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """path: a .ncu-rep, or the `ncu -i … --page raw --csv` text already made on the GPU box (capture.sh)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(out.splitlines()))
     hdr, units = r[0], r[1]
     idx = [hdr.index(w) for w in WANT if w in hdr]
     print("# selected metrics from %s (ncu --set full --clock-control none)" % path)
+
+    def num(row, name):
+        return float(row[hdr.index(name)].replace(",", "")) if name in hdr and row[hdr.index(name)] else 0.0
+
+    def scale(name, to):   # ncu picks the unit per column: normalise to bytes / ns
+        u = units[hdr.index(name)] if name in hdr else ""
+        return {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e3, "ms": 1e6, "ns": 1.0, "s": 1e9}.get(u, 1.0)
+
     for row in r[2:]:
+        if "Kernel Name" in hdr and "pcv::" not in row[hdr.index("Kernel Name")]:
+            continue    # torch's own kernels of the probe script (table normalisation, fills)
         for i in idx:
             print("  %s = %s %s" % (hdr[i], row[i], units[i]))
+        rd = num(row, "dram__bytes_read.sum") * scale("dram__bytes_read.sum", "byte")
+        wr = num(row, "dram__bytes_write.sum") * scale("dram__bytes_write.sum", "byte")
+        ns = num(row, "gpu__time_duration.sum") * scale("gpu__time_duration.sum", "ns")
+        l2 = num(row, "lts__t_bytes.sum") * scale("lts__t_bytes.sum", "byte")
+        if ns:
+            print("  derived: DRAM traffic %.3f MB -> %.1f GB/s achieved%s" % (
+                (rd + wr) / 1e6, (rd + wr) / ns, "; L2 traffic %.3f MB -> %.1f GB/s" % (l2 / 1e6, l2 / ns) if l2 else ""))
         print("  --")
 
 

@@ -1,6 +1,6 @@
-"""Embedding-dimension sweep of the greedy score+select: the exact SIMT engine at
-D in {8, 16, 32, 64, 128} and the tcgen05 filter engine at D=8, N=100000 items x M=4096 query rows.
-Prints CUDA-event time per call, logits/s and the contraction TFLOP/s."""
+"""Embedding-dimension sweep of the greedy score+select: the tcgen05 filter engine and the
+exact SIMT engine at D in {8, 16, 32, 64, 128}.  N x M from the command line (default 100000 items x 4096 rows;
+`1000000 20480` is the C4 shape).  Prints CUDA-event time per call, logits/s and the contraction TFLOP/s."""
 import os
 import sys
 
@@ -9,9 +9,11 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pivotcvae_b200 import ops  # noqa: E402
 
-N, M = 100000, 4096
+N, M = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (100000, 4096)
+ENGINES = sys.argv[3].split(",") if len(sys.argv) > 3 else ["tcgen05", "simt"]
 g = torch.Generator(device="cuda").manual_seed(0)
-for D, engine in [(8, "tcgen05"), (8, "simt"), (16, "simt"), (32, "simt"), (64, "simt"), (128, "simt")]:
+print("# N=%d items x M=%d rows" % (N, M))
+for D, engine in [(D, e) for D in (8, 16, 32, 64, 128) for e in ENGINES]:
     W = torch.nn.functional.normalize(torch.rand(N, D, generator=g, device="cuda") * 2 - 1, dim=1)
     Q = torch.randn(M, D, generator=g, device="cuda") * 0.5
     tab = ops.Table(W)

@@ -51,6 +51,42 @@ def test_tc_golden_dims8(ops, golden):
     assert np.array_equal(N(idx), fx["d8/idx"]) and np.array_equal(N(val), fx["d8/val"])   # == torch.mm + torch.max
 
 
+@pytest.mark.parametrize("D", [16, 32, 64, 128])
+def test_tc_golden_other_dims(ops, golden, D):
+    """--dim is free in the reference (train_generative.py:302): the tcgen05 filter walks D in k-atoms of 8."""
+    fx = golden("dims")
+    W, Q = fx["d%d/W" % D], fx["d%d/Q" % D]
+    tab = ops.Table(T(W))
+    idx, val = ops.score_select(tab, T(Q), "greedy", engine="tcgen05")
+    assert np.array_equal(N(idx), fx["d%d/idx" % D])       # the reference's torch.mm + torch.max indices
+    oi, ov = oracle.score_select(W, Q)
+    assert np.array_equal(N(idx), oi) and np.array_equal(N(val), ov)
+
+
+@pytest.mark.parametrize("n_items,M,D", [(256, 128, 16), (2049, 130, 16), (50000, 1024, 16), (4095, 77, 32), (65536, 300, 32),
+                                         (100003, 515, 64), (3707, 320, 64), (300, 1, 128), (40001, 700, 128), (9000, 129, 128)])
+def test_tc_other_dims_match_oracle(ops, n_items, M, D):
+    rng = np.random.default_rng(n_items * 7 + M + D)
+    W = _unit(rng, n_items, D)
+    Q = (rng.standard_normal((M, D)) * rng.uniform(0.05, 3.0, (M, 1))).astype(np.float32)
+    if n_items > 600:   # exact ties in different tiles / column slices, a tie block that overflows the lists
+        W[n_items - 1] = W[5]
+        W[n_items // 2 + 3] = W[5]
+        W[300] = W[5]
+        Q[0] = 1.7 * W[5]
+        W[400:400 + 150] = W[400]
+        Q[1 % M] = 2.0 * W[400]
+    tab = ops.Table(T(W))
+    idx, val = ops.score_select(tab, T(Q), "greedy", engine="tcgen05")
+    oi, ov = oracle.score_select(W, Q)
+    assert np.array_equal(N(idx), oi)
+    assert np.array_equal(N(val), ov)
+    si, sv = ops.score_select(tab, T(Q), "greedy", engine="simt")
+    assert torch.equal(idx, si) and torch.equal(val, sv)
+    ai, av = ops.score_select(tab, T(Q), "greedy", engine="auto")
+    assert torch.equal(idx, ai) and torch.equal(val, av)
+
+
 def test_tc_all_equal_and_heavy_ties(ops):
     """Every item inside the band: lists collapse continuously; the first index must still win."""
     W = np.tile(np.array([[0.5, 0.5, 0.5, 0.5, 0, 0, 0, 0]], dtype=np.float32), (5000, 1))
