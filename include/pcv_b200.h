@@ -85,7 +85,11 @@ typedef struct {
   const float *noise; /* exprace: [M, n_rows] Exp(1) draws (parity mode) or NULL   */
   uint64_t seed;      /* exprace with noise==NULL: Philox4x32-10 key               */
   uint64_t offset;    /* Philox stream offset (added to the row counter word)      */
-  int no_repeat;      /* reserved: must be 0 (the reference has no mask) */
+  int no_repeat;      /* 0 (default) = the reference's behaviour: independent per-row arg-max, duplicates inside a slate
+                         allowed (cvae.py:97-101).  L > 0 (opt-in extension, greedy mode, L <= 16, M % L == 0):
+                         rows are the L consecutive slots of M/L slates and slot l takes its best item that slots
+                         0..l-1 of the same slate have not taken (pcv_slate_no_repeat runs after the top-1 pass; the
+                         workspace must then hold pcv_score_select_workspace_bytes + pcv_score_topk_workspace_bytes) */
   const uint64_t *offset_dev; /* optional DEVICE counter added to `offset` at run time, so a
                                  captured CUDA graph draws fresh noise on every replay  */
 } pcv_select_opts;
@@ -117,6 +121,20 @@ int pcv_philox_exponential(uint64_t seed, uint64_t offset, int64_t M, int64_t n_
 int pcv_sigmoid_categorical(const pcv_table *t, const float *Q, int64_t M, uint64_t seed, uint64_t offset,
                             const uint64_t *offset_dev, int64_t *out_idx, int32_t *out_iters,
                             pcv_stream_t stream);
+/* Exact top-k over the catalog (torch.topk of the score row; models/deterministic.py:119 in the reference, and the
+ * building block of the no-repeat selection): out_idx/out_val [M, k], k <= 16, sorted by score descending, equal
+ * scores by ascending index; same fp32 sequential-k FMA chain as pcv_score_select; entries beyond the catalog size
+ * are -1 / -inf.  Indices are global (+ row_offset). */
+int pcv_score_topk_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
+int pcv_score_topk(const pcv_table *t, const float *Q, int64_t M, int k, int64_t *out_idx, float *out_val,
+                   void *workspace, size_t workspace_bytes, pcv_stream_t stream);
+/* Opt-in no-repeat slate selection (NOT reference behaviour; north_star's "already-chosen-item mask").
+ * Q: [B*L, dim] slot queries, items: [B*L] the top-1 picks of pcv_score_select (in/out), vals: optional [B*L]
+ * winning scores (in/out).  Slates whose picks contain a duplicate are re-selected sequentially: slot l takes its
+ * best item (ties -> lowest index) not taken by slots 0..l-1.  Only the rows of those slates are re-scored (exact
+ * top-L, one pass).  Workspace: pcv_score_topk_workspace_bytes(t, B*L).  The table must be the whole catalog. */
+int pcv_slate_no_repeat(const pcv_table *t, const float *Q, int64_t B, int L, int64_t *items, float *vals,
+                        void *workspace, size_t workspace_bytes, pcv_stream_t stream);
 /* Vocab-parallel merge: vals/idx are [G, M] partials gathered from G
  * shards in shard order; winner = max val, ties -> lowest global index. */
 int pcv_vp_merge_select(const float *vals, const int64_t *idx, int G, int64_t M,

@@ -175,6 +175,32 @@ def score_logits(W, Q):
     return out
 
 
+def score_topk(W, Q, k):
+    """torch.topk of every score row, restated: score descending, equal scores by ascending index (the order a
+    first-index arg-max repeated k times gives).  -> (idx int64[M, k], val f32[M, k])."""
+    p = score_logits(W, Q)
+    order = np.lexsort((np.broadcast_to(np.arange(p.shape[1]), p.shape), -p.astype(np.float64)), axis=1)[:, :k]
+    return order.astype(np.int64), np.take_along_axis(p, order, 1)
+
+
+def slate_no_repeat(W, Q, L):
+    """Opt-in no-repeat selection (NOT reference behaviour, SURVEY F1): rows of Q are the L slots of M/L slates;
+    slot l takes arg-max_j <q, w_j> (ties -> lowest j) over the items slots 0..l-1 of its slate have not taken."""
+    p = score_logits(W, Q)
+    M = p.shape[0]
+    items = np.empty(M, dtype=np.int64)
+    vals = np.empty(M, dtype=np.float32)
+    for b in range(M // L):
+        taken = []
+        for l in range(L):
+            row = p[b * L + l].copy()
+            row[taken] = -np.inf
+            j = int(np.argmax(row))            # numpy arg-max returns the first maximal index
+            items[b * L + l], vals[b * L + l] = j, row[j]
+            taken.append(j)
+    return items, vals
+
+
 def ce(W, Q, targets, bitmask=None):
     """-> (loss_rows[M], lse[M], dq[M, D]); bitmask None = full-catalog soft-max."""
     W, Q, targets = _f32(W), _f32(Q), _i64(targets).reshape(-1)

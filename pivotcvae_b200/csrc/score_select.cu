@@ -397,9 +397,29 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
                      void *workspace, size_t workspace_bytes, pcv_stream_t stream) {
   PCV_CHECK_ARG(th && Q && opts && out_idx, "NULL pointer");
   PCV_CHECK_ARG(M > 0, "M must be > 0");
-  PCV_CHECK_ARG(opts->no_repeat == 0, "no_repeat masks are not reference behaviour (SURVEY F1) and are not implemented");
   PCV_CHECK_ARG(opts->mode == PCV_SELECT_GREEDY || opts->mode == PCV_SELECT_EXPRACE, "bad mode");
   const Table *t = reinterpret_cast<const Table *>(th);
+  if (opts->no_repeat != 0) {
+    // opt-in extension (the reference has no mask): top-1 pass on the head of the workspace, then the
+    // duplicate-holding slates are re-selected sequentially by pcv_slate_no_repeat on the tail of it
+    const int Ls = opts->no_repeat;
+    PCV_CHECK_ARG(Ls >= 1 && Ls <= 16, "no_repeat must be the slate size (1..16)");
+    PCV_CHECK_ARG(opts->mode == PCV_SELECT_GREEDY, "no_repeat needs greedy mode");
+    PCV_CHECK_ARG(M % Ls == 0, "no_repeat: M must be a multiple of the slate size");
+    size_t head = 0, tail = 0;
+    int rc0 = pcv_score_select_workspace_bytes(th, M, &head);
+    if (rc0 == PCV_OK) rc0 = pcv_score_topk_workspace_bytes(th, M, &tail);
+    if (rc0 != PCV_OK) return rc0;
+    if (workspace == nullptr || workspace_bytes < head + tail) {
+      set_error("score_select(no_repeat): workspace too small (%zu < %zu + %zu)", workspace_bytes, head, tail);
+      return PCV_ERR_WORKSPACE;
+    }
+    pcv_select_opts o = *opts;
+    o.no_repeat = 0;
+    rc0 = pcv_score_select(th, Q, M, &o, out_idx, out_val, workspace, head, stream);
+    if (rc0 != PCV_OK) return rc0;
+    return pcv_slate_no_repeat(th, Q, M / Ls, Ls, out_idx, out_val, static_cast<char *>(workspace) + head, tail, stream);
+  }
   PCV_CHECK_ARG(t->n_rows < 0x7fffffffLL, "shard larger than 2^31-1 rows");
   int rc = check_arch();
   if (rc != PCV_OK) return rc;

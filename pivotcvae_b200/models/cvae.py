@@ -49,6 +49,10 @@ class BaseCVAE(nn.Module):
         # "race" = the exponential race over the whole catalog with in-kernel Philox noise (O(N) per row)
         self.pivot_sampler = "rejection"
         self.ce_engine = "exact"   # "tf32": full-catalog CE logits on the tensor cores (reduced-precision tolerance)
+        # Opt-in extension, OFF by default because the reference has no such logic (cvae.py:97-101 picks
+        # every slot independently, duplicates allowed).  True: a slot never repeats an item an earlier slot of
+        # the same slate took (sequential arg-max without replacement; include/pcv_b200.h pcv_slate_no_repeat).
+        self.no_repeat = False
         self._table = None
         self._full = None    # full-catalog handle while vocab-parallel (the sampler draws over every row)
         self._vp = None      # vocab-parallel state: (group, lo, hi) once enable_vocab_parallel() is called
@@ -179,6 +183,14 @@ class BaseCVAE(nn.Module):
     def get_recommended_item(self, embeddings):
         """arg-max item per row over the whole catalog (cvae.py:97-101) -> int64 (rows,)."""
         q = embeddings.reshape(-1, self.feature_size)
+        if getattr(self, "no_repeat", False):
+            if self._vp is not None:
+                raise L.PcvError("no_repeat selection is not available in vocab-parallel mode (it needs the whole "
+                                 "catalog on the rank)")
+            if q.shape[0] % self.slate_size:
+                raise L.PcvError("no_repeat: rows must be whole slates (multiple of slate_size)")
+            return ops.score_select(self.item_table(), q.detach(), "greedy", engine=self.select_engine, want_val=False,
+                                    no_repeat=self.slate_size)[0]
         return self._select(q.detach(), "greedy")
 
     def sample_encoding(self, s, r, u=None):

@@ -127,8 +127,16 @@ class Table:
             self._ws.move_to_end(key)
         if ws is None:
             n = ctypes.c_size_t()
-            fn = L.load().pcv_score_select_workspace_bytes if kind == "select" else L.load().pcv_ce_workspace_bytes
-            L.check(fn(self._h, int(M), ctypes.byref(n)), "workspace query")
+            lib = L.load()
+            fns = {"select": [lib.pcv_score_select_workspace_bytes], "ce": [lib.pcv_ce_workspace_bytes],
+                   "topk": [lib.pcv_score_topk_workspace_bytes],
+                   # no-repeat select: the top-1 workspace followed by the top-k one (include/pcv_b200.h)
+                   "select_nr": [lib.pcv_score_select_workspace_bytes, lib.pcv_score_topk_workspace_bytes]}[kind]
+            total = 0
+            for fn in fns:
+                L.check(fn(self._h, int(M), ctypes.byref(n)), "workspace query")
+                total += int(n.value)
+            n = ctypes.c_size_t(total)
             ws = torch.zeros(max(int(n.value), 256), dtype=torch.uint8, device=self.weight.device)  # zero-filled once (ABI contract)
             # least-recently-used eviction, one entry at a time; a workspace whose pointer a live CUDA graph
             # baked in is pinned by that graph object (pin_workspaces) and is never dropped
@@ -167,8 +175,9 @@ def counter_add(counter, inc):
 
 
 def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="auto", want_val=True,
-                 offset_dev=None):
-    """-> (idx int64[M], val f32[M]).  mode 'greedy' | 'exprace'."""
+                 offset_dev=None, no_repeat=0):
+    """-> (idx int64[M], val f32[M]).  mode 'greedy' | 'exprace'.  no_repeat=L (opt-in, NOT reference behaviour):
+    rows are the L slots of M/L slates; a slot never repeats an item an earlier slot of its slate took."""
     Q = _f32(Q, "Q")
     M, D = Q.shape
     if D != table.dim:
@@ -181,15 +190,44 @@ def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="
         if tuple(noise.shape) != (M, table.n_rows):
             raise L.PcvError("noise must be [M, n_rows]")
     opts.noise = noise.data_ptr() if noise is not None else None
-    opts.seed, opts.offset, opts.no_repeat = int(seed), int(offset), 0
+    opts.seed, opts.offset, opts.no_repeat = int(seed), int(offset), int(no_repeat)
     opts.offset_dev = offset_dev.data_ptr() if offset_dev is not None else None
     idx = torch.empty(M, dtype=torch.int64, device=Q.device)
     val = torch.empty(M, dtype=torch.float32, device=Q.device) if want_val else None
-    ws = table.workspace("select", M)
+    ws = table.workspace("select_nr" if no_repeat else "select", M)
     with torch.cuda.device(Q.device), _timed("score_select_%s_M%d" % (mode, M)):
         L.check(L.load().pcv_score_select(table.handle, _ptr(Q), M, ctypes.byref(opts), _ptr(idx), _ptr(val),
                                           _ptr(ws), ws.numel(), _stream()), "pcv_score_select")
     return idx, val
+
+
+def score_topk(table, Q, k):
+    """Exact top-k over the catalog -> (idx int64[M, k], val f32[M, k]), score descending, ties by ascending index."""
+    Q = _f32(Q, "Q")
+    M, D = Q.shape
+    if D != table.dim:
+        raise L.PcvError("Q has dim %d, table has dim %d" % (D, table.dim))
+    idx = torch.empty(M, k, dtype=torch.int64, device=Q.device)
+    val = torch.empty(M, k, dtype=torch.float32, device=Q.device)
+    ws = table.workspace("topk", M)
+    with torch.cuda.device(Q.device), _timed("score_topk_M%d" % M):
+        L.check(L.load().pcv_score_topk(table.handle, _ptr(Q), M, int(k), _ptr(idx), _ptr(val), _ptr(ws), ws.numel(),
+                                        _stream()), "pcv_score_topk")
+    return idx, val
+
+
+def slate_no_repeat(table, Q, items, slate_size, vals=None):
+    """In place: re-select the slates of `items` ([B*L] top-1 picks for the slot queries Q [B*L, D]) that contain a
+    duplicate, sequentially without replacement (opt-in extension; include/pcv_b200.h)."""
+    Q, items = _f32(Q, "Q"), _i64(items, "items")
+    M, D = Q.shape
+    if M % slate_size or items.numel() != M:
+        raise L.PcvError("items / Q rows must be B * slate_size")
+    ws = table.workspace("topk", M)
+    with torch.cuda.device(Q.device), _timed("slate_no_repeat_M%d" % M):
+        L.check(L.load().pcv_slate_no_repeat(table.handle, _ptr(Q), M // slate_size, int(slate_size), _ptr(items),
+                                             _ptr(vals), _ptr(ws), ws.numel(), _stream()), "pcv_slate_no_repeat")
+    return items
 
 
 def sigmoid_categorical(table, Q, seed=0, offset=0, offset_dev=None, want_iters=False):

@@ -208,3 +208,28 @@ def test_slate_metrics(golden):
     np.testing.assert_allclose(oracle.ils(fx["table"], fx["slates"]), fx["ils"], rtol=1e-5, atol=1e-6)
     assert abs(oracle.ils(fx["table"], fx["slates"])[3] - 1.0) < 1e-6
     assert oracle.coverage(fx["slates"], 900) == float(fx["coverage"])
+
+
+def test_oracle_topk_and_no_repeat_restatement():
+    """score_topk == torch.topk semantics on distinct scores and first-index order on ties; no-repeat = sequential
+    arg-max without replacement (an extension: the reference itself never masks)."""
+    import torch
+    rng = np.random.default_rng(3)
+    W = rng.standard_normal((400, 8)).astype(np.float32)
+    W /= np.linalg.norm(W, axis=1, keepdims=True)
+    Q = rng.standard_normal((30, 8)).astype(np.float32)
+    idx, val = oracle.score_topk(W, Q, 6)
+    p = torch.from_numpy(oracle.score_logits(W, Q))
+    tv, ti = torch.topk(p, 6, dim=1)
+    assert np.array_equal(idx, ti.numpy()) and np.array_equal(val, tv.numpy())
+    W[10] = W[3]
+    W[200] = W[3]
+    Q[0] = W[3]
+    idx, _ = oracle.score_topk(W, Q, 3)
+    assert list(idx[0]) == [3, 10, 200]
+    Q[1], Q[2] = Q[0], Q[0]
+    items, _ = oracle.slate_no_repeat(W, Q, 5)
+    assert list(items[:3]) == [3, 10, 200]
+    top1 = oracle.score_select(W, Q[5:10])[0]
+    if len(set(top1)) == 5:        # a slate without duplicates keeps the reference's independent picks
+        assert np.array_equal(items[5:10], top1)
