@@ -256,11 +256,24 @@ typedef struct {
 int pcv_ce_workspace_bytes(const pcv_table *t, int64_t M, size_t *bytes_host);
 /* Single streaming pass producing loss rows, log-sum-exp and dq (forward and
  * the gradient in one pass; backward is a scale by the upstream gradient).
- * (Vocab-parallel CE partials are not exposed yet: the table must have row_offset 0.) */
+ * The table must be the whole catalog (row_offset 0); shards go through pcv_ce_partials. */
 int pcv_ce_fwd_bwd(const pcv_table *t, const float *Q, const int64_t *targets,
                    int64_t M, const pcv_ce_mask *mask, float *loss_rows, float *lse,
                    float *dq, void *workspace, size_t workspace_bytes,
                    pcv_stream_t stream);
+
+/* Vocab-parallel CE: the same streaming pass over ONE row shard of the table (pcv_table_create with
+ * row_offset), full-catalog soft-max only (keep_prob >= 1; engine EXACT or TF32).  rec_out: [M, 2 + dim] per-row
+ * partial records {m, l, acc[dim]}: m = max logit over the shard, l = sum_j e^{x_j - m}, acc = sum_j e^{x_j - m} w_j.
+ * The caller all-gathers the records of the G shards (ONE collective of M * (2 + dim) floats per rank) and
+ * pcv_ce_vp_merge combines them: lse = M' + log sum_g l_g e^{m_g - M'}, loss = lse - <q, w_t>,
+ * dq = sum_g acc_g e^{m_g - M'} / L - w_t, with the target row taken from the WHOLE fp32 table W_full [N, dim]
+ * (every rank keeps it), exact FMA chain.  Every rank ends up with the full dq, so no further all-reduce is needed. */
+int pcv_ce_partials(const pcv_table *shard, const float *Q, const int64_t *targets, int64_t M,
+                    const pcv_ce_mask *mask, float *rec_out, void *workspace, size_t workspace_bytes,
+                    pcv_stream_t stream);
+int pcv_ce_vp_merge(const float *recs, int G, const float *W_full, int dim, const float *Q, const int64_t *targets,
+                    int64_t M, float *loss_rows, float *lse, float *dq, pcv_stream_t stream);
 
 /* Candidate-mode (sampled soft-max) CE — the reference's default training mode
  * (train_generative.py:52-56; pivotcvae.py:265-271, listcvae.py:157-163):

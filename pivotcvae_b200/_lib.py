@@ -91,6 +91,10 @@ EXPORTS = {
     "pcv_ce_workspace_bytes": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_size_t)]),
     "pcv_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(CeMask), c_void_p,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pcv_ce_partials": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(CeMask), c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
+    "pcv_ce_vp_merge": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     "pcv_cand_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     "pcv_mlp_packed_bytes": (ctypes.c_size_t, [c_int, c_int]),

@@ -139,6 +139,35 @@ class CatalogCEFn(torch.autograd.Function):
         return d, None, None, None, None, None, None, None, None
 
 
+class VocabParallelCEFn(torch.autograd.Function):
+    """The same mean CE with the catalog sharded over the ranks of `group`: local partial records over
+    this rank's row shard, ONE all-gather of [M, 2 + D] floats, merge.  Every rank gets the full loss and the full
+    d loss / d q, so the replicated MLPs see identical gradients without any further collective."""
+
+    @staticmethod
+    def forward(ctx, q, shard, full_weight, targets, group, engine="exact"):
+        import torch.distributed as dist
+        rec = ops.ce_partials(shard, q, targets, engine=engine)
+        world = dist.get_world_size(group)
+        recs = torch.empty(world * rec.shape[0], rec.shape[1], dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(recs, rec, group=group)
+        recs = recs.view(world, rec.shape[0], rec.shape[1])
+        loss_rows, lse, dq = ops.ce_vp_merge(recs, full_weight, q, targets, want_dq=q.requires_grad)
+        ctx.M = q.shape[0]
+        if dq is not None:
+            ctx.save_for_backward(dq)
+        ctx.mark_non_differentiable(lse)
+        return loss_rows.mean(), loss_rows, lse
+
+    @staticmethod
+    def backward(ctx, g_mean, g_rows, _g_lse):
+        (dq,) = ctx.saved_tensors
+        d = dq * (g_mean / ctx.M)
+        if g_rows is not None:
+            d = d + dq * g_rows.unsqueeze(1)
+        return d, None, None, None, None, None
+
+
 class KLFn(torch.autograd.Function):
     """-0.5 * sum(1 + lv - plv - (exp(lv) + (mu-pmu)^2)/exp(plv))  (train_generative.py:61)."""
 

@@ -220,7 +220,7 @@ __global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, 
                                    const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
                                    const float *__restrict__ Q, const int64_t *__restrict__ targets,
                                    float *__restrict__ loss_rows, float *__restrict__ lse_out,
-                                   float *__restrict__ dq) {
+                                   float *__restrict__ dq, float *__restrict__ rec_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   const int REC = 3 + D;
@@ -239,6 +239,22 @@ __global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, 
     if (rec[0] != -INFINITY) L += rec[1] * __expf(rec[0] - mx);
   }
   L += (float)n_out * __expf(-mx);
+  if (rec_out) {
+    // vocab-parallel shard: hand out the merged partial {m, l, acc[D]} of this shard's columns (no target terms);
+    // pcv_ce_vp_merge combines the shards' records after the all-gather
+    float *o = rec_out + i * (2 + D);
+    o[0] = mx;
+    o[1] = L;
+    for (int k = 0; k < D; ++k) {
+      float a = 0.f;
+      for (int s = 0; s < n_split; ++s) {
+        const float *rec = part + ((int64_t)s * M + i) * REC;
+        if (rec[0] != -INFINITY) a += rec[3 + k] * __expf(rec[0] - mx);
+      }
+      o[2 + k] = a;
+    }
+    return;
+  }
   const float lse = mx + logf(L);
   const int64_t t = targets[i] - row_offset;
   const float *wt = W + t * D;
@@ -254,6 +270,42 @@ __global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, 
       for (int s = 0; s < n_split; ++s) {
         const float *rec = part + ((int64_t)s * M + i) * REC;
         if (rec[0] != -INFINITY) a += rec[3 + k] * __expf(rec[0] - mx);
+      }
+      dq[i * D + k] = a * inv - wt[k];
+    }
+  }
+}
+
+// Vocab-parallel merge: recs = [G][M][2 + D] shard records {m, l, acc[D]} in any shard order
+// (the combination is symmetric); W is the WHOLE fp32 table (every rank keeps it: <= 320 MB), so the target logit
+// and the target row come from the exact chain as in the single-GPU finalize.
+__global__ void ce_vp_merge_kernel(const float *__restrict__ recs, int G, int64_t M, int D, const float *__restrict__ W,
+                                   const float *__restrict__ Q, const int64_t *__restrict__ targets,
+                                   float *__restrict__ loss_rows, float *__restrict__ lse_out, float *__restrict__ dq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int REC = 2 + D;
+  float mx = -INFINITY;
+  for (int g = 0; g < G; ++g) mx = fmaxf(mx, recs[((int64_t)g * M + i) * REC]);
+  float L = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float *rec = recs + ((int64_t)g * M + i) * REC;
+    if (rec[0] != -INFINITY) L += rec[1] * __expf(rec[0] - mx);
+  }
+  const float lse = mx + logf(L);
+  const float *wt = W + targets[i] * D;
+  const float *qi = Q + i * D;
+  float xt = 0.f;
+  for (int k = 0; k < D; ++k) xt = fmaf(qi[k], wt[k], xt);
+  if (loss_rows) loss_rows[i] = lse - xt;
+  if (lse_out) lse_out[i] = lse;
+  if (dq) {
+    const float inv = 1.f / L;
+    for (int k = 0; k < D; ++k) {
+      float a = 0.f;
+      for (int g = 0; g < G; ++g) {
+        const float *rec = recs + ((int64_t)g * M + i) * REC;
+        if (rec[0] != -INFINITY) a += rec[2 + k] * __expf(rec[0] - mx);
       }
       dq[i * D + k] = a * inv - wt[k];
     }
@@ -564,14 +616,18 @@ int pcv_ce_workspace_bytes(const pcv_table *th, int64_t M, size_t *bytes_host) {
   return PCV_OK;
 }
 
-int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, int64_t M,
-                   const pcv_ce_mask *mask, float *loss_rows, float *lse, float *dq,
-                   void *workspace, size_t workspace_bytes, pcv_stream_t stream) {
+static int ce_run(const pcv_table *th, const float *Q, const int64_t *targets, int64_t M,
+                  const pcv_ce_mask *mask, float *loss_rows, float *lse, float *dq, float *rec_out,
+                  void *workspace, size_t workspace_bytes, pcv_stream_t stream) {
   PCV_CHECK_ARG(th && Q && targets && mask, "NULL pointer");
   PCV_CHECK_ARG(M > 0, "M must be > 0");
   const Table *t = reinterpret_cast<const Table *>(th);
   PCV_CHECK_ARG(t->n_rows < 0x7fffffffLL, "shard larger than 2^31-1 rows");
-  PCV_CHECK_ARG(t->row_offset == 0, "vocab-parallel CE partials are not exposed yet: row_offset must be 0");
+  PCV_CHECK_ARG(rec_out != nullptr || t->row_offset == 0,
+                "a table shard (row_offset > 0) yields partial records: call pcv_ce_partials + pcv_ce_vp_merge");
+  PCV_CHECK_ARG(rec_out == nullptr || (mask->bitmask == nullptr && mask->keep_prob >= 1.0),
+                "pcv_ce_partials serves the full-catalog soft-max (keep_prob >= 1, no bitmask); the sparse mask "
+                "visits O(n_neg) columns per row and needs no sharding");
   PCV_CHECK_ARG(mask->keep_prob > 0.0, "keep_prob must be > 0");
   int rc = check_arch();
   if (rc != PCV_OK) return rc;
@@ -597,7 +653,7 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
     const int n_parts = ce_tc_launch(t, Q, M, part, workspace_bytes, st);
     if (n_parts < 0) return n_parts;
     ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(part, n_parts, M, t->dim, t->W, t->n_rows,
-                                                                    t->row_offset, Q, targets, loss_rows, lse, dq);
+                                                                    t->row_offset, Q, targets, loss_rows, lse, dq, rec_out);
     PCV_LAUNCH_CHECK();
     return PCV_OK;
   } else if (mask->keep_prob >= 1.0) {
@@ -617,7 +673,32 @@ int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, 
   }
   if (rc != PCV_OK) return rc;
   ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(
-      part, p.n_split, M, t->dim, t->W, t->n_rows, t->row_offset, Q, targets, loss_rows, lse, dq);
+      part, p.n_split, M, t->dim, t->W, t->n_rows, t->row_offset, Q, targets, loss_rows, lse, dq, rec_out);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+int pcv_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *targets, int64_t M,
+                   const pcv_ce_mask *mask, float *loss_rows, float *lse, float *dq,
+                   void *workspace, size_t workspace_bytes, pcv_stream_t stream) {
+  return ce_run(th, Q, targets, M, mask, loss_rows, lse, dq, nullptr, workspace, workspace_bytes, stream);
+}
+
+int pcv_ce_partials(const pcv_table *th, const float *Q, const int64_t *targets, int64_t M,
+                    const pcv_ce_mask *mask, float *rec_out, void *workspace, size_t workspace_bytes,
+                    pcv_stream_t stream) {
+  PCV_CHECK_ARG(rec_out != nullptr, "rec_out is NULL");
+  return ce_run(th, Q, targets, M, mask, nullptr, nullptr, nullptr, rec_out, workspace, workspace_bytes, stream);
+}
+
+int pcv_ce_vp_merge(const float *recs, int G, const float *W_full, int dim, const float *Q, const int64_t *targets,
+                    int64_t M, float *loss_rows, float *lse, float *dq, pcv_stream_t stream) {
+  PCV_CHECK_ARG(recs && W_full && Q && targets, "NULL pointer");
+  PCV_CHECK_ARG(G >= 1 && M > 0 && dim >= 4 && dim <= 128, "bad shape");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  ce_vp_merge_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(recs, G, M, dim, W_full, Q, targets,
+                                                                                    loss_rows, lse, dq);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }

@@ -283,7 +283,7 @@ static void ce_tc_plan(const Table *t, int64_t M, CeTcPlan *p) {
   p->ws_bytes = (size_t)p->n_split * TC_SLICES * (size_t)M * CE_TC_REC * sizeof(float);
 }
 
-bool ce_tc_supported(const Table *t) { return t->dim == TC_D && t->tmap_valid && t->row_offset == 0; }
+bool ce_tc_supported(const Table *t) { return t->dim == TC_D && t->tmap_valid; }
 
 size_t ce_tc_workspace(const Table *t, int64_t M) {
   if (!ce_tc_supported(t)) return 0;

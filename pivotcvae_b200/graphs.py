@@ -40,7 +40,14 @@ class GraphedSlateGenerator:
 
     def _step(self):
         items, z_mu = self.model.recommend(self.ctx, None if self.no_user else self.users, return_item=True)
-        resp = self.env(items.view(self.batch, -1), self.users)
+        sl = self.model._vp_row_slice(self.batch)
+        if sl is not None:      # vocab-parallel: the response model scores this rank's slates only, one all-gather
+            from .parallel import all_gather_rows
+            _, r0, per = sl
+            resp = all_gather_rows(self.env(items.view(self.batch, -1)[r0:r0 + per], self.users[r0:r0 + per]),
+                                   self.model._vp[0])
+        else:
+            resp = self.env(items.view(self.batch, -1), self.users)
         self.model.noise.end_graph_step()
         return items, z_mu, resp
 

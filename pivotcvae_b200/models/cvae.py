@@ -63,18 +63,46 @@ class BaseCVAE(nn.Module):
         st["_table"] = None
         st["_full"] = None
         st["_vp"] = None
+        st.pop("_rows", None)
         st.pop("_head_cache", None)
         return st
 
     # ---- vocab-parallel scoring: every rank keeps the full fp32 table (<= 320 MB) for the
     # gathers, but scores only its own 128-aligned row shard; one all-gather of (val, idx) per scoring step
-    def enable_vocab_parallel(self, group=None):
+    def enable_vocab_parallel(self, group=None, shard_rows=True):
+        """Score against this rank's row shard of the catalog only.  shard_rows (default): in recommend() the MLP
+        blocks run on this rank's 1/world slice of the batch instead of redundantly on all of it, and the
+        queries are all-gathered before every sharded scoring step (a few hundred KB over NVLink)."""
         import torch.distributed as dist
         from ..parallel import shard_bounds
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         lo, hi = shard_bounds(self.docEmbed.weight.shape[0], world, rank)
         self._vp = (group, lo, hi)
+        self._vp_rows = bool(shard_rows)
         self._table = None
+
+    def _vp_row_slice(self, B):
+        """(world, first row, rows per rank) when recommend() may shard its MLP rows over the vocab-parallel group:
+        throughput mode only (queued parity-mode noise tensors address the whole batch) and an evenly split batch."""
+        if self._vp is None or not getattr(self, "_vp_rows", False):
+            return None
+        if any(self.noise._queue[k] for k in ("eps", "race")):
+            return None
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self._vp[0]), dist.get_rank(self._vp[0])
+        if world == 1 or B % world:
+            return None
+        return world, rank * (B // world), B // world
+
+    def _stream_args(self, rows):
+        """Philox rows of one op.  While the MLP rows are sharded, every rank reserves the rows of the WHOLE batch and
+        draws those of its own slice, so the noise is exactly that of the unsharded run."""
+        sl = getattr(self, "_rows", None)
+        if sl is None:
+            return self.noise.stream_args(rows)
+        kw = self.noise.stream_args(sl[1])
+        kw["offset"] += sl[0]
+        return kw
 
     def _select(self, q, mode="greedy", **kw):
         """score+select over the (possibly sharded) catalog -> global item ids int64 (rows,)."""
@@ -159,7 +187,7 @@ class BaseCVAE(nn.Module):
         eps = self.noise.pop("eps")
         if eps is not None:
             return dict(eps=eps.to(self.docEmbed.weight.device))
-        return self.noise.stream_args(B)
+        return self._stream_args(B)
 
     # ---- reference API
     def reparametrize(self, mu, logvar):

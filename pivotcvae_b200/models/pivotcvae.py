@@ -70,7 +70,7 @@ class UserPivotCVAE(BaseCVAE):
             # throughput mode: the same Categorical(sigmoid(scores)) drawn exactly in O(1) per row (csrc/sampler.cu);
             # needs the whole catalog, which every vocab-parallel rank keeps anyway -> no collective
             from .. import ops
-            return ops.sigmoid_categorical(self.full_table(), q, **self.noise.stream_args(q.shape[0]))
+            return ops.sigmoid_categorical(self.full_table(), q, **self._stream_args(q.shape[0]))
         return self._select(q, "exprace", **self.noise.stream_args(q.shape[0]))
 
     def pick_pivot(self, pivot_output, true_pivot=[]):
@@ -129,6 +129,9 @@ class UserPivotCVAE(BaseCVAE):
         """prior -> z -> pivot -> slate completion -> arg-max items (pivotcvae.py:278-296)."""
         with torch.no_grad():
             r, u, _ = self._inputs(r, u)
+            sl = self._vp_row_slice(r.shape[0])
+            if sl is not None and (self.infer_pick == "max" or self.pivot_sampler == "rejection"):
+                return self._recommend_vp_rows(r, u, return_item, sl)
             # prior -> z -> PSM in one launch, pivot pick, SCM, per-slot arg-max
             out, z, pivot_output = self._prior_chain(r, u, self.psmMLP)
             user_seg = None if self.noUser else self._user_seg(u)
@@ -137,6 +140,35 @@ class UserPivotCVAE(BaseCVAE):
             res = self.get_recommended_item(rx) if return_item else rx.view(r.shape[0], self.slate_size, self.feature_size)
             self.noise.flush_eager()
             return res, z_mu
+
+    def _recommend_vp_rows(self, r, u, return_item, sl):
+        """Vocab-parallel recommend() with the MLP rows sharded too: this rank runs prior -> z -> PSM and the SCM on its
+        B/world rows, the queries are all-gathered ([pivot query | z_mu] once, rx once) and every scoring step is the
+        sharded select + all-reduce(MAX) of _select().  A sampled pivot needs no exchange at all: the rejection
+        sampler draws this rank's rows over the whole catalog, which every rank keeps."""
+        from ..parallel import all_gather_rows
+        world, r0, per = sl
+        group = self._vp[0]
+        B, Z, D = r.shape[0], self.latent_size, self.feature_size
+        rl = r[r0:r0 + per]
+        ul = None if u is None else u[r0:r0 + per]
+        self._rows = (r0, B)
+        try:
+            out, z, pivot_output = self._prior_chain(rl, ul, self.psmMLP)
+            if self.infer_pick == "max":
+                head = all_gather_rows(torch.cat([pivot_output, out[:, :Z]], 1), group)      # [B, D + Z]
+                pivot = self._select(head[:, :D].contiguous(), "greedy")[r0:r0 + per]
+                z_mu = head[:, D:]
+            else:
+                pivot = self._pick_index(pivot_output, None)
+                z_mu = all_gather_rows(out[:, :Z].contiguous(), group)
+            user_seg = None if self.noUser else self._user_seg(ul)
+            rx = all_gather_rows(self._scm(z, ("onehot", rl), pivot, user_seg, []), group)   # [B, L * D]
+        finally:
+            self._rows = None
+        res = self.get_recommended_item(rx) if return_item else rx.view(B, self.slate_size, D)
+        self.noise.flush_eager()
+        return res, z_mu
 
     def log(self, logger):
         for k, v in (("feature size", self.feature_size), ("slate size", self.slate_size),

@@ -513,6 +513,39 @@ def ce_fwd_bwd(table, Q, targets, keep_prob=1.0, bitmask=None, seed=0, offset=0,
     return loss, lse, dq
 
 
+def ce_partials(shard, Q, targets, engine="exact"):
+    """Vocab-parallel CE, local step: partial records [M, 2 + D] = {m, l, acc[D]} of this rank's row shard
+    (full-catalog soft-max); see include/pcv_b200.h pcv_ce_partials."""
+    Q, targets = _f32(Q, "Q"), _i64(targets, "targets").reshape(-1)
+    M, D = Q.shape
+    mask = L.CeMask()
+    mask.keep_prob = 1.0
+    mask.engine = 1 if engine == "tf32" else 0
+    rec = torch.empty(M, 2 + D, dtype=torch.float32, device=Q.device)
+    ws = shard.workspace("ce", M)
+    with torch.cuda.device(Q.device), _timed("ce_partials"):
+        L.check(L.load().pcv_ce_partials(shard.handle, _ptr(Q), _ptr(targets), M, ctypes.byref(mask), _ptr(rec), _ptr(ws),
+                                         ws.numel(), _stream()), "pcv_ce_partials")
+    return rec
+
+
+def ce_vp_merge(recs, W_full, Q, targets, want_dq=True):
+    """recs [G, M, 2 + D] gathered from the G shards -> (loss_rows[M], lse[M], dq[M, D] | None)."""
+    recs, W_full, Q = _f32(recs, "recs"), _f32(W_full, "W_full"), _f32(Q, "Q")
+    targets = _i64(targets, "targets").reshape(-1)
+    G, M, R = recs.shape
+    D = Q.shape[1]
+    if R != 2 + D or W_full.shape[1] != D:
+        raise L.PcvError("records must be [G, M, 2 + D]")
+    loss = torch.empty(M, dtype=torch.float32, device=Q.device)
+    lse = torch.empty(M, dtype=torch.float32, device=Q.device)
+    dq = torch.empty(M, D, dtype=torch.float32, device=Q.device) if want_dq else None
+    with torch.cuda.device(Q.device), _timed("ce_vp_merge"):
+        L.check(L.load().pcv_ce_vp_merge(_ptr(recs), G, _ptr(W_full), D, _ptr(Q), _ptr(targets), M, _ptr(loss), _ptr(lse),
+                                         _ptr(dq), _stream()), "pcv_ce_vp_merge")
+    return loss, lse, dq
+
+
 def cand_ce_fwd_bwd(table, Q, candidates, target_pos, want_dq=True, want_logits=False):
     """Sampled soft-max CE over per-row candidate lists -> (loss_rows[M], lse[M], dq[M,D]|None, p[M,nC]|None)."""
     Q = _f32(Q, "Q")

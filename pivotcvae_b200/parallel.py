@@ -43,6 +43,37 @@ def merge_partials(vals, idx):
     return best_i, best_v
 
 
+def all_gather_rows(t, group=None):
+    """[rows/world, C] on every rank -> [rows, C] in rank order (one NCCL all-gather, capturable in a CUDA graph)."""
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out
+
+
+def merge_ce_partials(recs, W_full, Q, targets):
+    """recs: [G, M, 2 + D] shard records {m, l, acc[D]} (see include/pcv_b200.h pcv_ce_partials).
+    -> (loss_rows[M], lse[M], dq[M, D]).  Pure torch restatement of pcv_ce_vp_merge for the CPU / gloo tests."""
+    m, l, acc = recs[..., 0], recs[..., 1], recs[..., 2:]
+    mx = m.max(0).values
+    w = torch.exp(m - mx)
+    Lsum = (l * w).sum(0)
+    lse = mx + torch.log(Lsum)
+    wt = W_full[targets]
+    xt = (Q * wt).sum(1)
+    dq = (acc * w.unsqueeze(-1)).sum(0) / Lsum.unsqueeze(1) - wt
+    return lse - xt, lse, dq
+
+
+def local_ce_partials(W_shard, Q):
+    """Torch stand-in of pcv_ce_partials for one row shard (CPU tests of the exchange): {m, l, acc[D]}."""
+    x = Q @ W_shard.t()
+    m = x.max(1).values
+    e = torch.exp(x - m.unsqueeze(1))
+    return torch.cat([m.unsqueeze(1), e.sum(1, keepdim=True), e @ W_shard], 1)
+
+
 class VocabParallelSelector:
     """score+select over a catalog sharded across the ranks of `group`.
 

@@ -50,10 +50,8 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
         KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
         model.noise.flush_eager()
         return recLoss + beta * KLD, recLoss, KLD
-    if getattr(model, "_vp", None) is not None:
-        raise NotImplementedError("vocab-parallel training (CE partials + dQ all-reduce) is not built yet; "
-                                  "train data-parallel with the replicated table")
-    table = model.item_table()
+    vp = getattr(model, "_vp", None)
+    table = model.full_table() if vp is not None else model.item_table()
     N = table.n_rows
     if n_neg > N:
         raise RuntimeError("n_neg (%d) > number of items (%d): torch.bernoulli would reject p > 1" % (n_neg, N))
@@ -63,8 +61,15 @@ def get_gen_loss(batch_data, model, lossFun, beta, n_neg=1000):
     kw = dict(seed=0, offset=0)
     if bitmask is None and keep < 1.0:
         kw = model.noise.stream_args(M)
-    recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, kw["seed"],
-                                      kw["offset"], kw.get("offset_dev"), getattr(model, "ce_engine", "exact"))
+    if vp is not None and bitmask is None and keep >= 1.0:
+        # vocab-parallel full-catalog soft-max: partial records over this rank's shard, one all-gather, merge
+        # (SURVEY §8e).  Masked training (keep < 1) touches O(n_neg) columns per row and stays unsharded below.
+        from .autograd import VocabParallelCEFn
+        recLoss, _, _ = VocabParallelCEFn.apply(rx.reshape(M, -1), model.item_table(), model.docEmbed.weight.detach(),
+                                                slates.reshape(-1), vp[0], getattr(model, "ce_engine", "exact"))
+    else:
+        recLoss, _, _ = CatalogCEFn.apply(rx.reshape(M, -1), table, slates.reshape(-1), keep, bitmask, kw["seed"],
+                                          kw["offset"], kw.get("offset_dev"), getattr(model, "ce_engine", "exact"))
     KLD = KLFn.apply(mu, logvar, pMu, pLogvar)
     loss = recLoss + beta * KLD
     model.noise.flush_eager()

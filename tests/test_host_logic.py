@@ -193,6 +193,42 @@ def test_vocab_parallel_gloo_world2(tmp_path):
     assert (tmp_path / "ok0").read_text() == "1" and (tmp_path / "ok1").read_text() == "1"
 
 
+def _vp_ce_worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import oracle
+    from pivotcvae_b200.parallel import local_ce_partials, merge_ce_partials, shard_bounds
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n_items, M, D = 777, 23, 8
+    W = rng.standard_normal((n_items, D)).astype(np.float32)
+    W /= np.linalg.norm(W, axis=1, keepdims=True)
+    Q = (2.0 * rng.standard_normal((M, D))).astype(np.float32)
+    tgt = rng.integers(0, n_items, M)
+    lo, hi = shard_bounds(n_items, world, rank)
+    rec = local_ce_partials(torch.from_numpy(W[lo:hi]), torch.from_numpy(Q))        # stand-in for pcv_ce_partials
+    recs = torch.empty(world * rec.shape[0], rec.shape[1])
+    dist.all_gather_into_tensor(recs, rec)                                          # the ONE collective of the step
+    recs = recs.view(world, rec.shape[0], rec.shape[1])
+    loss, lse, dq = merge_ce_partials(recs, torch.from_numpy(W), torch.from_numpy(Q), torch.from_numpy(tgt))
+    ol, olse, odq = oracle.ce(W, Q, tgt)
+    ok = (np.allclose(loss.numpy(), ol, rtol=1e-4, atol=1e-5) and np.allclose(lse.numpy(), olse, rtol=1e-4, atol=1e-5)
+          and np.allclose(dq.numpy(), odq, rtol=1e-3, atol=1e-5))
+    open(os.path.join(tmpdir, "ce_ok%d" % rank), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_vocab_parallel_ce_gloo_world2(tmp_path):
+    """Vocab-parallel training exchange on CPU: 2 ranks, gloo, one all-gather of {m, l, acc[D]} records, merged
+    loss / lse / dq == the unsharded oracle CE (1e-4)."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_vp_ce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ce_ok0").read_text() == "1" and (tmp_path / "ce_ok1").read_text() == "1"
+
+
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` (the unmodified reference from baseline/_ref on the host cores when that copy
     exists, else the oracle port) prints the contract line, with the SAME config dict as the GPU arm would."""
