@@ -529,8 +529,10 @@ def measure_train(D, args, wname, n_neg_arg, ce_engine, window_s, cpu_seconds=0.
     model.ce_engine = ce_engine
     n_neg = w["n_items"] if n_neg_arg <= 0 else n_neg_arg
     tf32 = ce_engine == "tf32" and n_neg >= w["n_items"]
-    # the reduced-precision training config also runs the MLP-gradient GEMMs in tf32
-    torch.backends.cuda.matmul.allow_tf32 = tf32
+    # the reduced-precision training config also runs the MLP-gradient GEMMs in one tf32 pass (own tcgen05 GEMMs,
+    # csrc/gemm_tc.cu); the fp32 config uses the same kernels with the 3xTF32 split
+    from pivotcvae_b200 import autograd as _ag
+    _ag.MLP_BWD_ENGINE = "tc" if tf32 else "tc3"
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=(world == 1))
     params = [p for p in model.parameters() if p.requires_grad]
     batches = [make_train_batch(w, B, i, seed=4321 + 7919 * rank) for i in range(K)]

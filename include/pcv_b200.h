@@ -223,6 +223,45 @@ int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_st
 size_t pcv_mlp_packed_bytes(int n_in, int n_out);
 int pcv_mlp_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* Tensor-core GEMMs of the MLP blocks' backward (and forward Linear)  */
+/*   train_generative.py:133 loss.backward() through pivotcvae.py:159-174, 204-240: */
+/*   the reference runs cuBLAS sgemm + elementwise autograd kernels.   */
+/* C[M, N] = A[M, K] . B[N, K]^T ("TN": both operands row-major with K contiguous, fp32, 16-byte aligned, leading */
+/* dimensions multiples of 4 floats), tcgen05 kind::tf32 with fp32 accumulation in TMEM, operands fed by TMA tensor */
+/* maps (ragged M / N / K are zero-filled by the TMA unit).  With A_lo / B_lo (= x - tf32(x)) three MMAs per k-step */
+/* (hi*hi + lo*hi + hi*lo, "3xTF32") give fp32-grade products.                                                     */
+/* Epilogue, in this order: + bias[n]; act; * act'(dact_src[m, n]) (derivative taken from a saved post-activation */
+/* output); store C (and its tf32 residual C_lo), optional transposed copy Ct [N, M] (+ Ct_lo).  split_k > 1: slice z */
+/* (K cut in 32-float blocks) writes raw partial sums to C + z * c_split_stride (pcv_wgrad_reduce adds them up).   */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  const float *A, *A_lo; int64_t lda;
+  const float *B, *B_lo; int64_t ldb;
+  int64_t M, N, K;
+  int split_k;
+  float *C; int64_t ldc; int64_t c_split_stride;
+  float *C_lo;
+  float *Ct, *Ct_lo; int64_t ldct;
+  const float *bias;
+  int act;
+  const float *dact_src; int64_t ld_dact; int dact;
+} pcv_gemm_desc;
+int pcv_gemm_tn(const pcv_gemm_desc *d, pcv_stream_t stream);
+/* Batched transposes (<= 12 per launch): dst[c, r] = src[r, c]; optional dst_lo = tf32 residual of the transposed copy, */
+/* optional src_lo [rows, ld_src] = tf32 residual of the source.  Lays out the saved activations / weights of an MLP   */
+/* block K-major for the weight-gradient and input-gradient GEMMs.                                                      */
+typedef struct {
+  const float *src; int64_t ld_src; int rows, cols;
+  float *dst; int64_t ld_dst;
+  float *dst_lo;
+  float *src_lo;
+} pcv_transpose_job;
+int pcv_transpose_batch(const pcv_transpose_job *jobs, int n_jobs, pcv_stream_t stream);
+/* dW[o, i] = sum_z part[z][o][i] in fixed order (deterministic), db[o] = sum_b Gt[o, b] (Gt = transposed output gradient). */
+int pcv_wgrad_reduce(const float *part, int n_split, int64_t split_stride, int64_t ld_part, int n_out, int n_in, float *dW,
+                     int64_t ld_dw, const float *Gt, int64_t ld_gt, int64_t B, float *db, pcv_stream_t stream);
+
 /* KL(q || p) between diagonal Gaussians, summed over batch and latent
  * (train_generative.py:61) plus analytic grads (any grad pointer may be NULL).
  * kl_out: device scalar (overwritten, not accumulated). */

@@ -58,6 +58,18 @@ class CeMask(ctypes.Structure):
                 ("offset", c_uint64), ("offset_dev", c_void_p), ("engine", c_int)]
 
 
+class GemmDesc(ctypes.Structure):
+    _fields_ = [("A", c_void_p), ("A_lo", c_void_p), ("lda", c_int64), ("B", c_void_p), ("B_lo", c_void_p), ("ldb", c_int64),
+                ("M", c_int64), ("N", c_int64), ("K", c_int64), ("split_k", c_int), ("C", c_void_p), ("ldc", c_int64),
+                ("c_split_stride", c_int64), ("C_lo", c_void_p), ("Ct", c_void_p), ("Ct_lo", c_void_p), ("ldct", c_int64),
+                ("bias", c_void_p), ("act", c_int), ("dact_src", c_void_p), ("ld_dact", c_int64), ("dact", c_int)]
+
+
+class TransposeJob(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("ld_src", c_int64), ("rows", c_int), ("cols", c_int), ("dst", c_void_p),
+                ("ld_dst", c_int64), ("dst_lo", c_void_p), ("src_lo", c_void_p)]
+
+
 class UrmDesc(ctypes.Structure):
     _fields_ = [("variant", c_int), ("doc_table", c_void_p), ("user_table", c_void_p),
                 ("item_bias", c_void_p), ("user_bias", c_void_p), ("pos_bias", c_void_p),
@@ -87,6 +99,10 @@ EXPORTS = {
     "pcv_vp_unpack_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pcv_mlp_fwd": (c_int, [ctypes.POINTER(MlpDesc), c_int64, c_void_p]),
     "pcv_mlp_fwd2": (c_int, [ctypes.POINTER(MlpDesc), ctypes.POINTER(MlpDesc), c_int64, c_void_p]),
+    "pcv_gemm_tn": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
+    "pcv_transpose_batch": (c_int, [ctypes.POINTER(TransposeJob), c_int, c_void_p]),
+    "pcv_wgrad_reduce": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                 c_void_p, c_void_p]),
     "pcv_kl_fwd_bwd": (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 5 + [c_void_p]),
     "pcv_ce_workspace_bytes": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_size_t)]),
     "pcv_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(CeMask), c_void_p,

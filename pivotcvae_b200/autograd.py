@@ -1,10 +1,15 @@
 """autograd glue around the fused CUDA blocks.
 
 Forward passes are single calls into libpcv_b200.so.  Backward of the catalog
-cross-entropy is free (the forward kernel already produced d loss/d q); backward
-of the small MLP blocks is a handful of plain GEMMs over saved activations,
-issued through torch.mm (cuBLAS) — plain library GEMMs, not part of the fused
-hot path.  The PSM block never needs a backward.
+cross-entropy is free (the forward kernel already produced d loss/d q).  Backward
+of the MLP blocks runs on the library's own tensor-core GEMMs (csrc/gemm_tc.cu):
+per layer one split-K weight-gradient GEMM (+ a deterministic reduce that also
+emits the bias gradient) and one input-gradient GEMM whose epilogue applies the
+activation derivative and writes the transposed copy the next weight-gradient
+GEMM consumes.  MLP_BWD_ENGINE = "tc3" (3xTF32: fp32-grade products, default),
+"tc" (one tf32 pass: the reduced-precision training config) or "torch" (the
+legacy torch.mm path, kept for A/B checks).  The PSM block never needs a backward
+(SURVEY F6).
 """
 import torch
 
@@ -38,6 +43,70 @@ class MlpSpec:
             else:
                 out.append(ops.Gather(s[1], s[2], normalize=(len(s) > 3 and s[3])))
         return out
+
+
+MLP_BWD_ENGINE = "tc3"
+
+
+def _padded(rows, cols, like):
+    """[rows, cols] view of a fresh buffer whose leading dimension is a multiple of 4 floats (TMA operand rule)."""
+    return torch.empty(rows, ops.pad4(cols), dtype=torch.float32, device=like.device)
+
+
+def _mlp_backward_tc(g, x0, acts, Ws, act_ids, need_input_grad, split3):
+    """Backward of Linear/activation chain on the tcgen05 GEMMs.  g: [B, n_out_last] gradient w.r.t. the last layer's
+    PRE-activation output (callers fold a last-layer activation in beforehand).  Returns (grads_wb, g_in | None)."""
+    nl = len(Ws)
+    B = g.shape[0]
+    Bp = ops.pad4(B)
+    inputs = [x0] + list(acts)                       # input of layer l (post-activation output of layer l - 1)
+    # ---- one batched launch: K-major (transposed) copies of every saved input, of the top gradient and of the weights
+    jobs, XT, XTlo, WT, WTlo = [], [], [], [None] * nl, [None] * nl
+    for l in range(nl):
+        n_in = Ws[l].shape[1]
+        xt = torch.empty(n_in, Bp, dtype=torch.float32, device=g.device)
+        xl = torch.empty_like(xt) if split3 else None
+        jobs.append(dict(src=inputs[l], rows=B, cols=n_in, dst=xt, dst_lo=xl))
+        XT.append(xt)
+        XTlo.append(xl)
+        if l > 0 or need_input_grad:
+            n_out = Ws[l].shape[0]
+            wt = _padded(n_in, n_out, g)
+            wl = torch.empty_like(wt) if split3 else None
+            jobs.append(dict(src=Ws[l], rows=n_out, cols=n_in, dst=wt, dst_lo=wl))
+            WT[l], WTlo[l] = wt, wl
+    n_top = Ws[-1].shape[0]
+    gp = _padded(B, n_top, g)
+    gp[:, :n_top].copy_(g)
+    gt = torch.empty(n_top, Bp, dtype=torch.float32, device=g.device)
+    gp_lo = torch.empty_like(gp) if split3 else None
+    gt_lo = torch.empty_like(gt) if split3 else None
+    jobs.append(dict(src=gp, rows=B, cols=n_top, dst=gt, dst_lo=gt_lo, src_lo=gp_lo))
+    ops.transpose_batch(jobs)
+    grads_wb = [None] * (2 * nl)
+    g_in = None
+    for l in range(nl - 1, -1, -1):
+        n_out, n_in = Ws[l].shape
+        tiles = -(-n_out // 128) * -(-n_in // 128)
+        splits = max(1, min(-(-B // 128), 148 // tiles, 32))
+        part = torch.empty(splits, n_out, ops.pad4(n_in), dtype=torch.float32, device=g.device)
+        ops.gemm_tn(gt, XT[l], n_out, n_in, B, A_lo=gt_lo, B_lo=XTlo[l], C=part, split_k=splits)
+        dW = torch.empty(n_out, n_in, dtype=torch.float32, device=g.device)
+        db = torch.empty(n_out, dtype=torch.float32, device=g.device)
+        ops.wgrad_reduce(part, n_out, n_in, dW, Gt=gt, B=B, db=db)
+        grads_wb[2 * l], grads_wb[2 * l + 1] = dW, db
+        if l == 0 and not need_input_grad:
+            break
+        nxt = _padded(B, n_in, g)
+        nxt_lo = torch.empty_like(nxt) if split3 else None
+        nxt_t = torch.empty(n_in, Bp, dtype=torch.float32, device=g.device) if l > 0 else None
+        nxt_t_lo = torch.empty_like(nxt_t) if (split3 and l > 0) else None
+        ops.gemm_tn(gp, WT[l], B, n_in, n_out, A_lo=gp_lo, B_lo=WTlo[l], C=nxt, C_lo=nxt_lo if l > 0 else None, Ct=nxt_t,
+                    Ct_lo=nxt_t_lo, dact_src=acts[l - 1] if l > 0 else None, dact=act_ids[l - 1] if l > 0 else 0)
+        if l == 0:
+            g_in = nxt
+        gp, gp_lo, gt, gt_lo = nxt, nxt_lo, nxt_t, nxt_t_lo
+    return grads_wb, g_in
 
 
 def _act_grad(g, a_out, act):
@@ -100,13 +169,18 @@ class FusedMLPFn(torch.autograd.Function):
             return (None,) * (3 + ctx.n_dense + 2 * nl)
         g = g.contiguous()
         grads_wb = [None] * (2 * nl)
-        for l in range(nl - 1, -1, -1):
-            a_out = out[:, c0:c0 + ctx.n_out] if l == nl - 1 else acts[l]
-            g = _act_grad(g, a_out, spec.acts[l])
-            a_prev = x0 if l == 0 else acts[l - 1]
-            grads_wb[2 * l] = g.t().mm(a_prev)
-            grads_wb[2 * l + 1] = g.sum(0)
-            g = g.mm(Ws[l])
+        if MLP_BWD_ENGINE != "torch":
+            g = _act_grad(g, out[:, c0:c0 + ctx.n_out], spec.acts[nl - 1])      # identity for every block of the path
+            need_in = any(s[0] == "dense" and ctx.needs_input_grad[3 + s[1]] for s in spec.segs)
+            grads_wb, g = _mlp_backward_tc(g, x0, acts, Ws, spec.acts, need_in, MLP_BWD_ENGINE == "tc3")
+        else:
+            for l in range(nl - 1, -1, -1):
+                a_out = out[:, c0:c0 + ctx.n_out] if l == nl - 1 else acts[l]
+                g = _act_grad(g, a_out, spec.acts[l])
+                a_prev = x0 if l == 0 else acts[l - 1]
+                grads_wb[2 * l] = g.t().mm(a_prev)
+                grads_wb[2 * l + 1] = g.sum(0)
+                g = g.mm(Ws[l])
         d_dense = [None] * ctx.n_dense
         for si, s in enumerate(spec.segs):
             if s[0] == "dense" and ctx.needs_input_grad[3 + s[1]]:

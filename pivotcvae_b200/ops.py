@@ -474,6 +474,62 @@ def mlp_forward_chain(first, second_builder, B):
 
 
 # ----------------------------------------------------------------------------
+# tensor-core GEMMs of the MLP blocks (csrc/gemm_tc.cu)
+# ----------------------------------------------------------------------------
+def pad4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+def gemm_tn(A, B, M, N, K, *, A_lo=None, B_lo=None, C=None, C_lo=None, Ct=None, Ct_lo=None, bias=None, act=0,
+            dact_src=None, dact=0, split_k=1):
+    """C[M, N] = A[M, K] . B[N, K]^T on the tensor cores (tf32; 3xTF32 when the residual operands are given).
+    A / B are 2-D fp32 CUDA tensors whose row stride is a multiple of 4 floats (they may be wider than K: padded
+    leading dimension).  Outputs are written into the given buffers (row strides taken from them); with split_k > 1
+    C is [split_k, M, ldc] raw partial sums."""
+    d = L.GemmDesc()
+    d.A, d.lda, d.B, d.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+    d.A_lo = A_lo.data_ptr() if A_lo is not None else None
+    d.B_lo = B_lo.data_ptr() if B_lo is not None else None
+    d.M, d.N, d.K, d.split_k = int(M), int(N), int(K), int(split_k)
+    if C is not None:
+        d.C, d.ldc = C.data_ptr(), C.stride(-2)
+        d.c_split_stride = C.stride(0) if split_k > 1 else 0
+    d.C_lo = C_lo.data_ptr() if C_lo is not None else None
+    if Ct is not None:
+        d.Ct, d.ldct = Ct.data_ptr(), Ct.stride(0)
+    d.Ct_lo = Ct_lo.data_ptr() if Ct_lo is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.act = int(act)
+    if dact_src is not None:
+        d.dact_src, d.ld_dact, d.dact = dact_src.data_ptr(), dact_src.stride(0), int(dact)
+    with torch.cuda.device(A.device), _timed("gemm_tn"):
+        L.check(L.load().pcv_gemm_tn(ctypes.byref(d), _stream()), "pcv_gemm_tn")
+
+
+def transpose_batch(jobs):
+    """jobs: list of dict(src=[rows, >=cols] tensor, rows, cols, dst=[cols, >=rows] tensor, dst_lo=None, src_lo=None)."""
+    for i in range(0, len(jobs), 12):
+        chunk = jobs[i:i + 12]
+        arr = (L.TransposeJob * len(chunk))()
+        for a, j in zip(arr, chunk):
+            a.src, a.ld_src, a.rows, a.cols = j["src"].data_ptr(), j["src"].stride(0), int(j["rows"]), int(j["cols"])
+            a.dst, a.ld_dst = j["dst"].data_ptr(), j["dst"].stride(0)
+            a.dst_lo = j["dst_lo"].data_ptr() if j.get("dst_lo") is not None else None
+            a.src_lo = j["src_lo"].data_ptr() if j.get("src_lo") is not None else None
+        with torch.cuda.device(chunk[0]["src"].device):
+            L.check(L.load().pcv_transpose_batch(arr, len(chunk), _stream()), "pcv_transpose_batch")
+
+
+def wgrad_reduce(part, n_out, n_in, dW, Gt=None, B=0, db=None):
+    """dW[n_out, n_in] = sum over the split-K slices of part [S, n_out, ld]; db[n_out] = row sums of Gt [n_out, >=B]."""
+    S = part.shape[0]
+    with torch.cuda.device(part.device):
+        L.check(L.load().pcv_wgrad_reduce(_ptr(part), S, part.stride(0), part.stride(1), int(n_out), int(n_in), _ptr(dW),
+                                          dW.stride(0), _ptr(Gt), Gt.stride(0) if Gt is not None else 0, int(B), _ptr(db),
+                                          _stream()), "pcv_wgrad_reduce")
+
+
+# ----------------------------------------------------------------------------
 # KL, CE, response models
 # ----------------------------------------------------------------------------
 def kl_fwd_bwd(mu, logvar, pmu, plogvar, grads=True):
