@@ -76,8 +76,11 @@ def _mlp_backward_tc(g, x0, acts, Ws, act_ids, need_input_grad, split3):
             jobs.append(dict(src=Ws[l], rows=n_out, cols=n_in, dst=wt, dst_lo=wl))
             WT[l], WTlo[l] = wt, wl
     n_top = Ws[-1].shape[0]
-    gp = _padded(B, n_top, g)
-    gp[:, :n_top].copy_(g)
+    if n_top % 4 == 0 and g.is_contiguous() and g.data_ptr() % 16 == 0:
+        gp = g                                       # already a legal TMA operand
+    else:
+        gp = _padded(B, n_top, g)
+        gp[:, :n_top].copy_(g)
     gt = torch.empty(n_top, Bp, dtype=torch.float32, device=g.device)
     gp_lo = torch.empty_like(gp) if split3 else None
     gt_lo = torch.empty_like(gt) if split3 else None

@@ -567,7 +567,7 @@ static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const in
 // tensor-core engine (ce_tc.cu)
 bool ce_tc_supported(const Table *t);
 size_t ce_tc_workspace(const Table *t, int64_t M);
-int ce_tc_launch(const Table *t, const float *Q, int64_t M, float *part, size_t ws_bytes, cudaStream_t st);
+int ce_tc_launch(const Table *t, const float *Q, const int64_t *targets, int64_t M, float *part, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace pcv
 
@@ -650,7 +650,7 @@ static int ce_run(const pcv_table *th, const float *Q, const int64_t *targets, i
       set_error("ce: the tf32 engine needs dim 8 and an unsharded table");
       return PCV_ERR_UNSUPPORTED;
     }
-    const int n_parts = ce_tc_launch(t, Q, M, part, workspace_bytes, st);
+    const int n_parts = ce_tc_launch(t, Q, targets, M, part, workspace_bytes, st);
     if (n_parts < 0) return n_parts;
     ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(part, n_parts, M, t->dim, t->W, t->n_rows,
                                                                     t->row_offset, Q, targets, loss_rows, lse, dq, rec_out);

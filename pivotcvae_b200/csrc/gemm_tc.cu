@@ -36,7 +36,10 @@ constexpr int GM_TILE_FLOATS = GM_BM * GM_BK;
 template <bool SPLIT3>
 struct GemmCfg {
   static constexpr int STAGES = SPLIT3 ? 3 : 4;
-  static constexpr size_t SMEM = (size_t)STAGES * (SPLIT3 ? 4 : 2) * GM_TILE_BYTES + 1024;
+  // + epilogue staging (4 warps x 32 x 33 floats) and, in the one-pass mode, room to prefetch the 128 x 128 tile of
+  // saved activations (act' epilogue) while the main loop runs
+  static constexpr size_t SMEM = (size_t)STAGES * (SPLIT3 ? 4 : 2) * GM_TILE_BYTES + 4 * 32 * 33 * 4 +
+                                 (SPLIT3 ? 0 : 4 * 128 * 33 * 4) + 1024;
 };
 struct GemmBars {
   unsigned long long full[GM_MAX_STAGES], empty[GM_MAX_STAGES], tfull;
@@ -155,18 +158,36 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       umma_commit(&Bq.tfull);
     }
   } else {
-    // ---------------- epilogue: thread = output row ----------------
+    // ---------------- epilogue: TMEM lane = output row; global traffic is made coalesced through a per-warp
+    // 32 x 33 staging tile: row-major data (C, the saved activation) moves with lane = column, the transposed copy
+    // (Ct) with lane = row
     const int quarter = warp & 3;
-    const int64_t m = (int64_t)m0 + quarter * 32 + lane;
+    const int ew = warp - 2;
+    float (*stage)[33] = reinterpret_cast<float (*)[33]>(tiles + (size_t)GM_STAGES * (SPLIT3 ? 4 : 2) * GM_TILE_FLOATS) + ew * 32;
+    const int64_t mb = (int64_t)m0 + quarter * 32;      // first row of this warp
+    const int64_t m = mb + lane;
     const bool row_ok = m < P.M;
+    float (*dpre)[33] = stage + (4 - ew) * 32 + ew * 128;   // per-warp [4 chunks x 32 rows][33], behind the staging tiles
+    const bool prefetched = !SPLIT3 && P.dact_src != nullptr;
+    if (prefetched) {
+      for (int c = 0; c < GM_BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= P.N || mb >= P.M) break;
+        const bool col_ok = nb + lane < P.N;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)
+          dpre[c * 32 + rr][lane] = (mb + rr < P.M && col_ok) ? __ldg(P.dact_src + (mb + rr) * P.ld_dact + nb + lane) : 0.f;
+      }
+      __syncwarp();
+    }
     mbar_wait(&Bq.tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float *Cz = P.C ? P.C + (int64_t)blockIdx.z * P.c_split_stride : nullptr;
-    const bool vec_ok = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < GM_BN / 32; ++c) {
       const int nb = n0 + c * 32;
-      if (nb >= P.N) break;          // warp-uniform
+      if (nb >= P.N || mb >= P.M) break;          // warp-uniform
+      const bool col_ok = nb + lane < P.N;
       uint32_t v[32];
       if (nkb > 0) {
         TC_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32));
@@ -182,31 +203,18 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (P.bias && nb + i < P.N) x += __ldg(P.bias + nb + i);
         o[i] = gm_act(x, P.act);
       }
-      if (P.dact_src && row_ok) {
-        const float *src = P.dact_src + m * P.ld_dact + nb;
+      if (prefetched) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < P.N) o[i] *= gm_dact(__ldg(src + i), P.dact);
-      }
-      if (row_ok && Cz) {
-        float *dst = Cz + m * P.ldc + nb;
-        if (vec_ok && nb + 32 <= P.N) {
+        for (int i = 0; i < 32; ++i) o[i] *= gm_dact(dpre[c * 32 + lane][i], P.dact);
+      } else if (P.dact_src) {
+        // saved[m, nb + lane]: one coalesced 128-byte row per instruction, turned to lane = row through the stage
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)
+          stage[rr][lane] = (mb + rr < P.M && col_ok) ? __ldg(P.dact_src + (mb + rr) * P.ld_dact + nb + lane) : 0.f;
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-          if (P.C_lo) {
-            float *dl = P.C_lo + m * P.ldc + nb;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4 *>(dl + i) = make_float4(tf32_lo(o[i]), tf32_lo(o[i + 1]), tf32_lo(o[i + 2]), tf32_lo(o[i + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < P.N) {
-              dst[i] = o[i];
-              if (P.C_lo) P.C_lo[m * P.ldc + nb + i] = tf32_lo(o[i]);
-            }
-        }
+        for (int i = 0; i < 32; ++i) o[i] *= gm_dact(stage[lane][i], P.dact);
+        __syncwarp();
       }
       if (P.Ct && row_ok) {
 #pragma unroll
@@ -215,6 +223,29 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             P.Ct[(int64_t)(nb + i) * P.ldct + m] = o[i];
             if (P.Ct_lo) P.Ct_lo[(int64_t)(nb + i) * P.ldct + m] = tf32_lo(o[i]);
           }
+      }
+      const bool direct = Cz && !P.Ct && !P.dact_src && !P.C_lo && (P.ldc % 4 == 0) && nb + 32 <= P.N &&
+                          ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+      if (direct) {
+        // plain tile (split-K partials): 128 contiguous bytes per thread, vector stores straight from the registers
+        if (row_ok) {
+          float *dst = Cz + m * P.ldc + nb;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+      } else if (Cz) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stage[lane][i] = o[i];
+        __syncwarp();
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          if (mb + rr < P.M && col_ok) {
+            const float x = stage[rr][lane];
+            Cz[(mb + rr) * P.ldc + nb + lane] = x;
+            if (P.C_lo) P.C_lo[(mb + rr) * P.ldc + nb + lane] = tf32_lo(x);
+          }
+        }
+        __syncwarp();
       }
     }
   }

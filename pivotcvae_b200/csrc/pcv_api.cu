@@ -56,6 +56,7 @@ __global__ void counter_add_kernel(unsigned long long *c, unsigned long long inc
 
 int table_init_tc(Table *t);  // score_select_tc.cu
 void table_free_tc(Table *t);
+void table_free_ce(Table *t);   // ce_tc2.cu
 
 }  // namespace pcv
 
@@ -108,6 +109,7 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
   t->row_offset = row_offset;
   t->tmap_valid = 0;
   t->packed = nullptr;
+  t->packed_t = nullptr;
   cudaGetDevice(&t->device);
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, t->device);
   // one-off: max row norm (error bound of the tf32 filter) + TMA descriptor
@@ -145,6 +147,7 @@ void pcv_table_destroy(pcv_table *th) {
   Table *t = reinterpret_cast<Table *>(th);
   if (!t) return;
   table_free_tc(t);
+  table_free_ce(t);
   delete t;
 }
 

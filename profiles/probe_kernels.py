@@ -10,6 +10,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("PCV_LIB"):          # A/B runs: load another build of the library (profiles/_trace/)
+    from pivotcvae_b200 import _lib
+    _lib.LIB_PATH = os.environ["PCV_LIB"]
 from pivotcvae_b200 import ops  # noqa: E402
 from pivotcvae_b200.env.response_model import URM_P_MR, UserResponseModel_MLP  # noqa: E402
 from pivotcvae_b200.models.pivotcvae import PIVOTCVAE_MODELS  # noqa: E402
@@ -113,7 +116,7 @@ def p_metrics():     # slate_metrics_kernel: gather L rows + ILS + coverage bitm
           "TB/s (algorithmic)")
 
 
-def p_ce_tc():       # ce_tc_kernel at C3 (tf32 logits, dense mask)
+def p_ce_tc():       # ce_tc2_kernel at C3 (tf32 logits and gradient on the tensor cores, dense mask)
     W, Q = table(100000), torch.randn(20480, 8, generator=G, device=DEV) * 0.5
     tab = ops.Table(W)
     tgt = torch.randint(0, 100000, (20480,), generator=G, device=DEV)
@@ -142,6 +145,24 @@ def p_cand_ce():     # cand_ce_kernel: sampled-softmax CE over 1000 candidates p
     pos = torch.zeros(20480, dtype=torch.int64, device=DEV)
     timed("cand_ce 20480 x 1000", lambda: ops.cand_ce_fwd_bwd(tab, Q, cand, pos), 20480 * 1000 * 40 / 1e3,
           "TB/s (ids + gathered rows)")
+
+
+def p_gemm_dx():     # gemm_tn_tc_kernel, input-gradient shape: G[4096, 256] . (W^T)[256, 256]^T, act' epilogue + transposed copy
+    Bsz, n = 4096, 256
+    Gm = torch.randn(Bsz, n, generator=G, device=DEV)
+    Wt = torch.randn(n, n, generator=G, device=DEV)
+    saved = torch.randn(Bsz, n, generator=G, device=DEV)
+    C, Ct = torch.empty(Bsz, n, device=DEV), torch.empty(n, Bsz, device=DEV)
+    timed("gemm dX 4096x256x256", lambda: ops.gemm_tn(Gm, Wt, Bsz, n, n, C=C, Ct=Ct, dact_src=saved, dact=1),
+          2.0 * Bsz * n * n / 1e3, "TFLOP/s")
+
+
+def p_gemm_dw():     # weight-gradient shape: G^T[256, 4096] . (X^T)[256, 4096]^T, split-K 32
+    Bsz, n = 4096, 256
+    Gt = torch.randn(n, Bsz, generator=G, device=DEV)
+    Xt = torch.randn(n, Bsz, generator=G, device=DEV)
+    part = torch.empty(32, n, n, device=DEV)
+    timed("gemm dW 256x256x4096 /32", lambda: ops.gemm_tn(Gt, Xt, n, n, Bsz, C=part, split_k=32), 2.0 * Bsz * n * n / 1e3, "TFLOP/s")
 
 
 ALL = {k[2:]: v for k, v in list(globals().items()) if k.startswith("p_")}

@@ -365,7 +365,7 @@ def test_ce_vocab_parallel_partials_merge(ops, n_items, M, G, engine):
     # |q| ~ 8.5 here: the tf32 logits carry ~2^-10 |q| of absolute error, so the reduced-precision engine is held
     # to 1e-3 against the fp32 oracle (the sharded-vs-unsharded comparison above is the vocab-parallel claim)
     lt = 1e-3 if engine == "tf32" else 1e-4
-    assert np.allclose(N(loss), ol, rtol=lt, atol=1e-4) and np.allclose(N(dq), odq, rtol=5e-3 if engine == "tf32" else 2e-3, atol=2e-4)
+    assert np.allclose(N(loss), ol, rtol=lt, atol=1e-4) and np.allclose(N(dq), odq, rtol=5e-3 if engine == "tf32" else 2e-3, atol=1e-3 if engine == "tf32" else 2e-4)
     # the torch restatement used by the gloo CPU test agrees with the kernel
     pl, ps, pd = merge_ce_partials(recs, Wt, Qt, tt)
     assert np.allclose(N(pl), N(loss), rtol=1e-5, atol=1e-5) and np.allclose(N(pd), N(dq), rtol=1e-4, atol=1e-6)
