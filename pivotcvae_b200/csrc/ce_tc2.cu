@@ -61,19 +61,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// The MMA warp runs CONVERGED: all 32 lanes execute the issue loop and one elected lane issues each tcgen05
-// instruction.  With a single-lane branch around the loop the compiler moves every operand vector -> uniform register
-// (R2UR) per MMA, ~25 instructions of latency-bound single-thread code per 8-cycle gradient MMA; converged, the
-// descriptors stay in uniform registers and an MMA costs a few uniform adds.
-__device__ __forceinline__ void umma_tf32_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
+// (the MMA warp runs converged: see umma_tf32_elect in tc_common.cuh)
 __device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -83,15 +71,6 @@ __device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tme
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit_elect(void *bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "elect.sync _|q, 0xffffffff;\n"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-      "}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
 #define C2_ST32(taddr, v)                                                                                   \
   asm volatile(                                                                                             \
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                       \
@@ -320,7 +299,7 @@ ce_tc2_kernel(const float *__restrict__ Wsw, const float *__restrict__ Wt, int64
           mbar_wait(&S.tempty[buf], ((gt / C2_BUFS) & 1) ^ 1);
           mbar_wait(&S.full[s], (gt / C2_STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          umma_tf32_ss_elect(tmem + buf * C2_BN, adesc, umma_desc_sw32(S.w[s]), C2_IDESC_S, 0);
+          umma_tf32_elect(tmem + buf * C2_BN, adesc, umma_desc_sw32(S.w[s]), C2_IDESC_S, 0);
           umma_commit_elect(&S.tfull[buf]);
           if (t > 1) grad_mma(gt - 2, t == 2);
         }

@@ -138,7 +138,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp, converged; one elected lane issues (tc_common.cuh: umma_tf32_elect)
       for (int i = 0; i < nkb; ++i) {
         const int s = i % GM_STAGES;
         mbar_wait(&Bq.full[s], (i / GM_STAGES) & 1);
@@ -147,15 +147,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < GM_BK / 8; ++j) {   // one k-step = 8 fp32 = 32 B inside the 128-byte swizzle row
           const uint64_t da = umma_desc_sw128(sa + j * 32), db = umma_desc_sw128(sb + j * 32);
-          umma_tf32(tmem, da, db, GM_IDESC, (i | j) != 0);
+          umma_tf32_elect(tmem, da, db, GM_IDESC, (i | j) != 0);
           if (SPLIT3) {
-            umma_tf32(tmem, umma_desc_sw128(smem_u32(tile_alo(s)) + j * 32), db, GM_IDESC, 1);
-            umma_tf32(tmem, da, umma_desc_sw128(smem_u32(tile_blo(s)) + j * 32), GM_IDESC, 1);
+            umma_tf32_elect(tmem, umma_desc_sw128(smem_u32(tile_alo(s)) + j * 32), db, GM_IDESC, 1);
+            umma_tf32_elect(tmem, da, umma_desc_sw128(smem_u32(tile_blo(s)) + j * 32), GM_IDESC, 1);
           }
         }
-        umma_commit(&Bq.empty[s]);
+        umma_commit_elect(&Bq.empty[s]);
       }
-      umma_commit(&Bq.tfull);
+      umma_commit_elect(&Bq.tfull);
     }
   } else {
     // ---------------- epilogue: TMEM lane = output row; global traffic is made coalesced through a per-warp

@@ -304,8 +304,8 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
     }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (the whole warp, converged; one elected lane issues: tc_common.cuh) ----------------
+    {
       uint32_t gt = 0, gs = 0;
       int it = 0;
       for (int ch = 0; ch < n_chunks; ++ch) {
@@ -337,13 +337,13 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
             // one k-step (8 fp32 = 32 B) per k-atom: the descriptors step by whole atoms (4 KB of A, 8 KB of B)
 #pragma unroll
             for (int a = 0; a < C::KS; ++a)
-              umma_tf32(tmem + buf * TC_BN, adesc + (uint64_t)(((kg * C::KS + a) * C::ATOM_A * 4) >> 4),
-                        umma_desc_sw32(S.b[s] + a * C::ATOM_B), TC_IDESC, (kg | a) != 0);
-            umma_commit(&S.empty[s]);
+              umma_tf32_elect(tmem + buf * TC_BN, adesc + (uint64_t)(((kg * C::KS + a) * C::ATOM_A * 4) >> 4),
+                              umma_desc_sw32(S.b[s] + a * C::ATOM_B), TC_IDESC, (kg | a) != 0);
+            umma_commit_elect(&S.empty[s]);
           }
-          umma_commit(&S.tfull[buf]);
+          umma_commit_elect(&S.tfull[buf]);
         }
-        umma_commit(&S.aempty[ab]);   // fires when every MMA of this item has read the A tile
+        umma_commit_elect(&S.aempty[ab]);   // fires when every MMA of this item has read the A tile
       }
       }
     }
