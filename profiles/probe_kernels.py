@@ -50,6 +50,18 @@ def p_select():      # score_select_tc_kernel + tc_refine_kernel at C4
     timed("select_c4 (1M x 20480)", lambda: ops.score_select(tab, Q, "greedy"), 1e6 * 20480 / 1e3, "T logits/s")
 
 
+def p_select_d128():   # the same filter at D = 128 (16 accumulating MMAs per tile): tensor-pipe evidence
+    W, Q = table(1000000, 128), torch.randn(20480, 128, generator=G, device=DEV) * 0.5
+    tab = ops.Table(W)
+    timed("select D=128 (1M x 20480)", lambda: ops.score_select(tab, Q, "greedy", engine="tcgen05"), 2 * 128 * 1e6 * 20480 / 1e3, "TFLOP/s")
+
+
+def p_topk():        # exact top-10 over 50k items for 2048 rows (the no-repeat re-selection path)
+    W, Q = table(50000), torch.randn(2048, 8, generator=G, device=DEV) * 0.5
+    tab = ops.Table(W)
+    timed("topk 10 (50k x 2048)", lambda: ops.score_topk(tab, Q, 10), 5e4 * 2048 / 1e3, "T logits/s")
+
+
 def p_select_c2():
     W, Q = table(50000), torch.randn(10240, 8, generator=G, device=DEV) * 0.5
     tab = ops.Table(W)
