@@ -736,7 +736,8 @@ __global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, i
 int table_init_tc(Table *t) {
   t->tmap_valid = 0;
   t->packed = nullptr;
-  t->tc_chunk_tiles = 4096;     // 4096 tiles x 8 KB = 32 MB of the pre-swizzled table per column chunk
+  // 32 MB of the pre-swizzled table per column chunk: 4096 tiles of 8 KB at D = 8, fewer (larger) tiles beyond
+  t->tc_chunk_tiles = 4096 / (t->dim >= 8 ? t->dim / 8 : 1);
   if (const char *e = getenv("PCV_TC_CHUNK_TILES")) {   // test hook: force chunking on small catalogs
     const int v = atoi(e);
     if (v >= 1) t->tc_chunk_tiles = v;

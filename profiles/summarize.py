@@ -61,7 +61,7 @@ def full(path):
         return {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e3, "ms": 1e6, "ns": 1.0, "s": 1e9}.get(u, 1.0)
 
     for row in r[2:]:
-        if "Kernel Name" in hdr and "pcv::" not in row[hdr.index("Kernel Name")]:
+        if "Kernel Name" in hdr and ("at::" in row[hdr.index("Kernel Name")] or "cub::" in row[hdr.index("Kernel Name")]):
             continue    # torch's own kernels of the probe script (table normalisation, fills)
         for i in idx:
             print("  %s = %s %s" % (hdr[i], row[i], units[i]))
