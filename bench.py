@@ -423,8 +423,9 @@ def measure_generate(D, args, wname, mode, window_s, vp=False, full=True, cpu_se
     if vp:
         out["slates_equal_1gpu"] = vp_equal
         out["scaling"] = "strong"
-        out["parallelism"] = ("vp%d (catalog rows sharded: one all-reduce(MAX) of int64 keys per scoring step; MLP / response rows "
-                              "sharded: all-gathers of the queries and scores; everything inside the step graph)" % world)
+        out["parallelism"] = ("vp%d (per-slot scoring: catalog rows sharded, one all-reduce(MAX) of int64 keys; MLP blocks, pivot pick "
+                              "and response model: batch rows sharded, one all-gather of [rx | z_mu] and one of the scores; "
+                              "3 NCCL collectives per step, all inside the step graph)" % world)
 
     # ---- roofline of the dominant kernel: the per-slot score+select over the catalog.  Events cannot sit inside
     # a graph replay, so the call alone (its kernels, on the decoder's own queries) is captured as its own graph

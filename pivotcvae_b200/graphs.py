@@ -36,6 +36,8 @@ class GraphedSlateGenerator:
             self.items, self.z_mu, self.resp = self._step()
         self.launches_per_step = ops.launch_count() - l0
         model.item_table().pin_workspaces()     # their pointers are baked into the graph
+        if getattr(model, "_vp", None) is not None:
+            model.full_table().pin_workspaces()  # vocab-parallel: the row-parallel pivot pick scores the whole catalog
         ops.pin_packed()
 
     def _step(self):

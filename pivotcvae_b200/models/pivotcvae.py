@@ -142,10 +142,12 @@ class UserPivotCVAE(BaseCVAE):
             return res, z_mu
 
     def _recommend_vp_rows(self, r, u, return_item, sl):
-        """Vocab-parallel recommend() with the MLP rows sharded too: this rank runs prior -> z -> PSM and the SCM on its
-        B/world rows, the queries are all-gathered ([pivot query | z_mu] once, rx once) and every scoring step is the
-        sharded select + all-reduce(MAX) of _select().  A sampled pivot needs no exchange at all: the rejection
-        sampler draws this rank's rows over the whole catalog, which every rank keeps."""
+        """Vocab-parallel recommend() with the MLP rows sharded too.  This rank runs prior -> z -> PSM -> pivot pick ->
+        SCM on its B/world rows; the pivot pick (1/(L+1) of the scoring work) is row-parallel against the whole
+        catalog, which every rank keeps anyway (<= 320 MB), so it needs no exchange — greedy and sampled alike.  ONE
+        all-gather then carries [rx | z_mu] of every rank, and the per-slot scoring (L/(L+1) of the work) is the
+        catalog-sharded select + all-reduce(MAX) of _select()."""
+        from .. import ops
         from ..parallel import all_gather_rows
         world, r0, per = sl
         group = self._vp[0]
@@ -156,16 +158,15 @@ class UserPivotCVAE(BaseCVAE):
         try:
             out, z, pivot_output = self._prior_chain(rl, ul, self.psmMLP)
             if self.infer_pick == "max":
-                head = all_gather_rows(torch.cat([pivot_output, out[:, :Z]], 1), group)      # [B, D + Z]
-                pivot = self._select(head[:, :D].contiguous(), "greedy")[r0:r0 + per]
-                z_mu = head[:, D:]
+                pivot = ops.score_select(self.full_table(), pivot_output, "greedy", engine=self.select_engine, want_val=False)[0]
             else:
                 pivot = self._pick_index(pivot_output, None)
-                z_mu = all_gather_rows(out[:, :Z].contiguous(), group)
             user_seg = None if self.noUser else self._user_seg(ul)
-            rx = all_gather_rows(self._scm(z, ("onehot", rl), pivot, user_seg, []), group)   # [B, L * D]
+            rx_local = self._scm(z, ("onehot", rl), pivot, user_seg, [])
         finally:
             self._rows = None
+        both = all_gather_rows(torch.cat([rx_local, out[:, :Z]], 1), group)          # [B, L * D + Z]
+        rx, z_mu = both[:, :rx_local.shape[1]].contiguous(), both[:, rx_local.shape[1]:]
         res = self.get_recommended_item(rx) if return_item else rx.view(B, self.slate_size, D)
         self.noise.flush_eager()
         return res, z_mu
