@@ -348,6 +348,21 @@ int pcv_urm_fwd(const pcv_urm_desc *d, const int64_t *slates, const int64_t *use
                 int64_t B, float *out, pcv_stream_t stream);
 
 /* ------------------------------------------------------------------ */
+/* Response-model pre-training (pretrain_env.py:25-139):  */
+/* the embeddings are trainable there, so the gather + normalise prologue */
+/* of env/response_model.py:76-83 needs a backward.                      */
+/* ------------------------------------------------------------------ */
+/* x0[b, :] = [ normalize(concat_l doc[slates[b, l]]) | normalize(usr[users[b]]) ] (usr NULL = no_user); x0 is
+ * [B, ld], inv_norm [B, 2] keeps 1 / max(|raw|, 1e-12) of both segments for the backward. */
+int pcv_gather_norm_fwd(const float *doc, const float *usr, const int64_t *slates, const int64_t *users, int64_t B, int L,
+                        int D, float *x0, int64_t ld, float *inv_norm, pcv_stream_t stream);
+/* d_doc / d_usr (zero-initialised by the caller, same shapes as the tables) += the gradient of x0 w.r.t. the raw rows. */
+int pcv_gather_norm_bwd(const float *g, int64_t ldg, const float *x0, int64_t ld, const float *inv_norm, const int64_t *slates,
+                        const int64_t *users, int64_t B, int L, int D, float *d_doc, float *d_usr, pcv_stream_t stream);
+/* nn.BCELoss()(sigmoid(pred), target) (pretrain_env.py:57-58,84; logs clamped at -100) and dpred (optional). */
+int pcv_bce_sigmoid(const float *pred, const float *target, int64_t n, float *loss, float *dpred, pcv_stream_t stream);
+
+/* ------------------------------------------------------------------ */
 /* Slate metrics of the variation-control evaluation (analysis.py:5-30) */
 /* ------------------------------------------------------------------ */
 /* ils[b] = (sum_{i,j} cos(e_i, e_j) - L) / (L (L-1)) over the L items of slate b (get_ILS);

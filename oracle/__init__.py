@@ -425,3 +425,65 @@ def ils(table, slates):
 def coverage(slates, N):
     """analysis.py:5-11 get_coverage."""
     return len(np.unique(np.asarray(slates))) * 1.0 / N
+
+
+# ---------------------------------------------------------------------------
+# SURVEY 8f N4: response-model pre-training step (pretrain_env.py:76-88) and the biased MF (deterministic.py:97-124)
+# ---------------------------------------------------------------------------
+def resp_train_step(sd, slates, users, resp, no_user):
+    """forward (env/response_model.py:76-87) -> BCELoss(sigmoid(pred), resp) -> gradients of every parameter incl. the
+    embedding tables.  numpy float64 restatement (small cases only).  -> (loss, pred, {name: grad})."""
+    doc = sd["docEmbed.weight"].astype(np.float64)
+    B, Ls = slates.shape
+    D = doc.shape[1]
+    raw = doc[slates].reshape(B, Ls * D)
+    nrm = np.maximum(np.linalg.norm(raw, axis=1, keepdims=True), 1e-12)
+    parts, raws, norms = [raw / nrm], [raw], [nrm]
+    if not no_user:
+        usr = sd["userEmbed.weight"].astype(np.float64)
+        ur = usr[users.reshape(-1)]
+        un = np.maximum(np.linalg.norm(ur, axis=1, keepdims=True), 1e-12)
+        parts.append(ur / un)
+        raws.append(ur)
+        norms.append(un)
+    x0 = np.concatenate(parts, 1)
+    n_layers = _count_layers(sd, "mlp")
+    acts, h = [x0], x0
+    for i in range(1, n_layers + 1):
+        h = h @ sd["mlp_%d.weight" % i].astype(np.float64).T + sd["mlp_%d.bias" % i].astype(np.float64)
+        if i < n_layers:
+            h = np.maximum(h, 0.0)
+        acts.append(h)
+    pred = h
+    s = 1.0 / (1.0 + np.exp(-pred))
+    t = resp.astype(np.float64)
+    loss = float(np.mean(-(t * np.maximum(np.log(s), -100) + (1 - t) * np.maximum(np.log(1 - s), -100))))
+    g = (s - t) / pred.size
+    grads = {}
+    for i in range(n_layers, 0, -1):
+        if i < n_layers:
+            g = g * (acts[i] > 0)
+        grads["mlp_%d.weight" % i] = g.T @ acts[i - 1]
+        grads["mlp_%d.bias" % i] = g.sum(0)
+        g = g @ sd["mlp_%d.weight" % i].astype(np.float64)
+    def unnorm(gx, xhat, nrm):  # noqa: E306
+        return (gx - xhat * (xhat * gx).sum(1, keepdims=True)) / nrm
+    gd = unnorm(g[:, :Ls * D], parts[0], norms[0]).reshape(B, Ls, D)
+    d_doc = np.zeros_like(doc)
+    np.add.at(d_doc, slates, gd)
+    grads["docEmbed.weight"] = d_doc
+    if not no_user:
+        gu = unnorm(g[:, Ls * D:], parts[1], norms[1])
+        d_usr = np.zeros_like(sd["userEmbed.weight"].astype(np.float64))
+        np.add.at(d_usr, users.reshape(-1), gu)
+        grads["userEmbed.weight"] = d_usr
+    return loss, pred, grads
+
+
+def mf_scores(doc, usr, doc_bias, user_bias, users):
+    """p[i, j] = <normalize(usr)[u_i], normalize(doc)[j]> + b_u + b_j (deterministic.py:36-47, 97-112), float64."""
+    d = doc.astype(np.float64)
+    u = usr.astype(np.float64)
+    d = d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    u = u / np.maximum(np.linalg.norm(u, axis=1, keepdims=True), 1e-12)
+    return u[users] @ d.T + user_bias.astype(np.float64)[users].reshape(-1, 1) + doc_bias.astype(np.float64).reshape(1, -1)

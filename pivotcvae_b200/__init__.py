@@ -15,18 +15,19 @@ def install_dropin():
     reference scripts, notebooks and whole-model pickles resolve to the B200 path."""
     import types
 
-    from . import train_generative
+    from . import pretrain_env, train_generative
     from .env import response_model
-    from .models import cvae, listcvae, pivotcvae
+    from .models import cvae, deterministic, listcvae, pivotcvae
 
     models_pkg = sys.modules.setdefault("models", types.ModuleType("models"))
     env_pkg = sys.modules.setdefault("env", types.ModuleType("env"))
-    for name, mod in (("cvae", cvae), ("pivotcvae", pivotcvae), ("listcvae", listcvae)):
+    for name, mod in (("cvae", cvae), ("pivotcvae", pivotcvae), ("listcvae", listcvae), ("deterministic", deterministic)):
         sys.modules["models." + name] = mod
         setattr(models_pkg, name, mod)
     sys.modules["env.response_model"] = response_model
     env_pkg.response_model = response_model
     sys.modules["train_generative"] = train_generative
+    sys.modules["pretrain_env"] = pretrain_env          # train_response_model (pretrain_env.py:25-139)
     # slate metrics (analysis.py:5-30): the reference module also holds ranking metrics that are not on the
     # path, so an importable reference `analysis` only gets its two slate metrics replaced
     from . import analysis as slate_metrics

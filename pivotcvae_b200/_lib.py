@@ -103,6 +103,10 @@ EXPORTS = {
     "pcv_transpose_batch": (c_int, [ctypes.POINTER(TransposeJob), c_int, c_void_p]),
     "pcv_wgrad_reduce": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                  c_void_p, c_void_p]),
+    "pcv_gather_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "pcv_gather_norm_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p]),
+    "pcv_bce_sigmoid": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pcv_kl_fwd_bwd": (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 5 + [c_void_p]),
     "pcv_ce_workspace_bytes": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_size_t)]),
     "pcv_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(CeMask), c_void_p,

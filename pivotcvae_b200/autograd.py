@@ -245,6 +245,41 @@ class VocabParallelCEFn(torch.autograd.Function):
         return d, None, None, None, None, None
 
 
+class GatherNormFn(torch.autograd.Function):
+    """x0 = [normalize(concat doc[slates]) | normalize(usr[users])] with trainable tables (the response model's
+    prologue, env/response_model.py:76-83, as pretrain_env.py trains it)."""
+
+    @staticmethod
+    def forward(ctx, doc, usr, slates, users):
+        x0, inv = ops.gather_norm_fwd(doc, usr, slates, users)
+        ctx.save_for_backward(x0, inv, slates, users if usr is not None else slates)
+        ctx.doc_shape, ctx.usr_shape = tuple(doc.shape), (tuple(usr.shape) if usr is not None else None)
+        return x0
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, inv, slates, users = ctx.saved_tensors
+        d_doc, d_usr = ops.gather_norm_bwd(g.contiguous(), x0, inv, slates, users, ctx.doc_shape, ctx.usr_shape)
+        return d_doc, d_usr, None, None
+
+
+class BCESigmoidFn(torch.autograd.Function):
+    """nn.BCELoss()(sigmoid(pred), target) in one kernel (pretrain_env.py:57-58, 84)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, dp = ops.bce_sigmoid(pred, target, want_grad=pred.requires_grad)
+        ctx.shape = pred.shape
+        if dp is not None:
+            ctx.save_for_backward(dp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return (dp * g).view(ctx.shape), None
+
+
 class KLFn(torch.autograd.Function):
     """-0.5 * sum(1 + lv - plv - (exp(lv) + (mu-pmu)^2)/exp(plv))  (train_generative.py:61)."""
 

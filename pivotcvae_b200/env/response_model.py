@@ -61,6 +61,8 @@ class UserResponseModel_MLP(Environment):
         -> Linear/ReLU chain -> (B, L) logits (response_model.py:76-87); one fused kernel."""
         slates, users = self._ids(slates, users)
         B = slates.shape[0]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(slates.reshape(B, -1), users)
         segs = [ops.Gather(self.docEmbed.weight.detach(), slates.reshape(B, -1), normalize=True)]
         if not self.noUser:
             segs.append(ops.Gather(self.userEmbed.weight.detach(), users.reshape(B, 1), normalize=True))
@@ -68,6 +70,19 @@ class UserResponseModel_MLP(Environment):
         layers = [(m.weight.detach(), m.bias.detach(), L.ACT_RELU if i < n - 1 else L.ACT_NONE)
                   for i, m in enumerate(self.mlp)]
         return ops.mlp_forward(segs, layers, B)["out"]
+
+
+    def _forward_train(self, slates, users):
+        """Differentiable path (pretrain_env.py:76-88 trains the embeddings too): gather + normalise with a backward,
+        then the fused MLP block with its tensor-core backward."""
+        from ..autograd import FusedMLPFn, GatherNormFn, MlpSpec
+        x0 = GatherNormFn.apply(self.docEmbed.weight, None if self.noUser else self.userEmbed.weight, slates, users)
+        n = len(self.mlp)
+        spec = MlpSpec([("dense", 0)], [L.ACT_RELU if i < n - 1 else L.ACT_NONE for i in range(n)], save=True)
+        flat = []
+        for m in self.mlp:
+            flat += [m.weight, m.bias]
+        return FusedMLPFn.apply(spec, slates.shape[0], 1, x0, *flat)
 
 
 class URM(Environment):

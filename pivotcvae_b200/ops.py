@@ -619,6 +619,46 @@ def cand_ce_fwd_bwd(table, Q, candidates, target_pos, want_dq=True, want_logits=
     return loss, lse, dq, p
 
 
+def gather_norm_fwd(doc, usr, slates, users):
+    """[normalize(concat doc[slates]) | normalize(usr[users])] -> (x0 [B, W], inv_norm [B, 2]); usr None = no user."""
+    doc, slates = _f32(doc, "doc table"), _i64(slates, "slates")
+    B, Ls = slates.shape
+    D = doc.shape[1]
+    W = (Ls + (0 if usr is None else 1)) * D
+    x0 = torch.empty(B, W, dtype=torch.float32, device=doc.device)
+    inv = torch.empty(B, 2, dtype=torch.float32, device=doc.device)
+    if usr is not None:
+        usr, users = _f32(usr, "user table"), _i64(users, "users").reshape(-1)
+    with torch.cuda.device(doc.device):
+        L.check(L.load().pcv_gather_norm_fwd(_ptr(doc), _ptr(usr), _ptr(slates), _ptr(users) if usr is not None else None, B, Ls, D,
+                                             _ptr(x0), W, _ptr(inv), _stream()), "pcv_gather_norm_fwd")
+    return x0, inv
+
+
+def gather_norm_bwd(g, x0, inv, slates, users, doc_shape, usr_shape):
+    """-> (d_doc, d_usr | None): gradient of the gather + normalise prologue scattered into table-shaped tensors."""
+    g = _f32(g, "g")
+    B, Ls = slates.shape
+    D = doc_shape[1]
+    d_doc = torch.zeros(doc_shape, dtype=torch.float32, device=g.device)
+    d_usr = torch.zeros(usr_shape, dtype=torch.float32, device=g.device) if usr_shape is not None else None
+    with torch.cuda.device(g.device):
+        L.check(L.load().pcv_gather_norm_bwd(_ptr(g), g.stride(0), _ptr(x0), x0.stride(0), _ptr(inv), _ptr(slates),
+                                             _ptr(users) if d_usr is not None else None, B, Ls, D, _ptr(d_doc), _ptr(d_usr),
+                                             _stream()), "pcv_gather_norm_bwd")
+    return d_doc, d_usr
+
+
+def bce_sigmoid(pred, target, want_grad=True):
+    """nn.BCELoss()(sigmoid(pred), target) -> (loss scalar tensor, dpred | None)."""
+    pred, target = _f32(pred, "pred").reshape(-1), _f32(target, "target").reshape(-1)
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    dp = torch.empty_like(pred) if want_grad else None
+    with torch.cuda.device(pred.device):
+        L.check(L.load().pcv_bce_sigmoid(_ptr(pred), _ptr(target), pred.numel(), _ptr(loss), _ptr(dp), _stream()), "pcv_bce_sigmoid")
+    return loss, dp
+
+
 def urm_forward(variant, doc, usr, item_bias, user_bias, slates, users, pos_bias=None, pos_dep=None, mr_factor=0.0):
     doc, usr = _f32(doc), _f32(usr)
     ib, ub = _f32(item_bias).reshape(-1), _f32(user_bias).reshape(-1)

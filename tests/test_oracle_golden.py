@@ -233,3 +233,24 @@ def test_oracle_topk_and_no_repeat_restatement():
     top1 = oracle.score_select(W, Q[5:10])[0]
     if len(set(top1)) == 5:        # a slate without duplicates keeps the reference's independent picks
         assert np.array_equal(items[5:10], top1)
+
+
+@pytest.mark.parametrize("tag,no_user", [("mlp_user", False), ("mlp_nouser", True)])
+def test_oracle_response_pretrain_step_vs_reference(golden, tag, no_user):
+    """the oracle's restatement of one pretrain_env.py training step == the reference's autograd."""
+    fx = golden("n4")
+    loss, pred, grads = oracle.resp_train_step(fx.sub(tag + "/sd/"), fx[tag + "/slates"], fx[tag + "/users"], fx[tag + "/resp"], no_user)
+    assert abs(loss - float(fx[tag + "/loss"])) <= 1e-6
+    np.testing.assert_allclose(pred, fx[tag + "/pred"], rtol=1e-5, atol=1e-6)
+    ref = fx.sub(tag + "/grad/")
+    assert set(ref) == set(grads)
+    for k, v in ref.items():
+        np.testing.assert_allclose(grads[k], v, rtol=1e-4, atol=1e-8, err_msg=k)
+
+
+def test_oracle_mf_scores_vs_reference(golden):
+    fx = golden("n4")
+    p = oracle.mf_scores(fx["mf/doc"], fx["mf/usr"], fx["mf/doc_bias"], fx["mf/user_bias"], fx["mf/users"])
+    np.testing.assert_allclose(p, fx["mf/p_all"], rtol=1e-5, atol=1e-6)
+    top = np.argsort(-p, axis=1, kind="stable")[:, :fx["mf/items"].shape[1]]
+    assert np.array_equal(top, fx["mf/items"])
