@@ -216,16 +216,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 32; ++i) o[i] *= gm_dact(stage[lane][i], P.dact);
         __syncwarp();
       }
-      if (P.Ct && row_ok) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < P.N) {
-            P.Ct[(int64_t)(nb + i) * P.ldct + m] = o[i];
-            if (P.Ct_lo) P.Ct_lo[(int64_t)(nb + i) * P.ldct + m] = tf32_lo(o[i]);
-          }
-      }
       const bool direct = Cz && !P.Ct && !P.dact_src && !P.C_lo && (P.ldc % 4 == 0) && nb + 32 <= P.N &&
                           ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+      // full, aligned 32 x 32 sub-tile: both layouts leave through the staging tile as 128-bit stores
+      const bool vec_tile = !direct && nb + 32 <= P.N && mb + 32 <= P.M &&
+                            (!Cz || ((P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                                     (!P.C_lo || (reinterpret_cast<uintptr_t>(P.C_lo) & 15) == 0))) &&
+                            (!P.Ct || ((P.ldct % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.Ct) & 15) == 0) &&
+                                       (!P.Ct_lo || (reinterpret_cast<uintptr_t>(P.Ct_lo) & 15) == 0)));
       if (direct) {
         // plain tile (split-K partials): 128 contiguous bytes per thread, vector stores straight from the registers
         if (row_ok) {
@@ -233,19 +231,57 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
         }
-      } else if (Cz) {
+      } else if (vec_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stage[lane][i] = o[i];
+        for (int i = 0; i < 32; ++i) stage[lane][i] = o[i];      // stage[row][col]
         __syncwarp();
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          if (mb + rr < P.M && col_ok) {
-            const float x = stage[rr][lane];
-            Cz[(mb + rr) * P.ldc + nb + lane] = x;
-            if (P.C_lo) P.C_lo[(mb + rr) * P.ldc + nb + lane] = tf32_lo(x);
+        const int sub = lane >> 3, q4 = (lane & 7) * 4;           // 4 rows (or columns) per instruction, 4 elements per lane
+        if (Cz) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            const float4 x = make_float4(stage[rr][q4], stage[rr][q4 + 1], stage[rr][q4 + 2], stage[rr][q4 + 3]);
+            *reinterpret_cast<float4 *>(Cz + (mb + rr) * P.ldc + nb + q4) = x;
+            if (P.C_lo)
+              *reinterpret_cast<float4 *>(P.C_lo + (mb + rr) * P.ldc + nb + q4) =
+                  make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+          }
+        }
+        if (P.Ct) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int cc = it * 4 + sub;                            // column of the tile = row of the transposed copy
+            const float4 x = make_float4(stage[q4][cc], stage[q4 + 1][cc], stage[q4 + 2][cc], stage[q4 + 3][cc]);
+            *reinterpret_cast<float4 *>(P.Ct + (int64_t)(nb + cc) * P.ldct + mb + q4) = x;
+            if (P.Ct_lo)
+              *reinterpret_cast<float4 *>(P.Ct_lo + (int64_t)(nb + cc) * P.ldct + mb + q4) =
+                  make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
           }
         }
         __syncwarp();
+      } else {
+        if (P.Ct && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < P.N) {
+              P.Ct[(int64_t)(nb + i) * P.ldct + m] = o[i];
+              if (P.Ct_lo) P.Ct_lo[(int64_t)(nb + i) * P.ldct + m] = tf32_lo(o[i]);
+            }
+        }
+        if (Cz) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stage[lane][i] = o[i];
+          __syncwarp();
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (mb + rr < P.M && col_ok) {
+              const float x = stage[rr][lane];
+              Cz[(mb + rr) * P.ldc + nb + lane] = x;
+              if (P.C_lo) P.C_lo[(mb + rr) * P.ldc + nb + lane] = tf32_lo(x);
+            }
+          }
+          __syncwarp();
+        }
       }
     }
   }

@@ -61,7 +61,7 @@ class UserResponseModel_MLP(Environment):
         -> Linear/ReLU chain -> (B, L) logits (response_model.py:76-87); one fused kernel."""
         slates, users = self._ids(slates, users)
         B = slates.shape[0]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if getattr(self, "differentiable", False) and torch.is_grad_enabled():
             return self._forward_train(slates.reshape(B, -1), users)
         segs = [ops.Gather(self.docEmbed.weight.detach(), slates.reshape(B, -1), normalize=True)]
         if not self.noUser:
@@ -71,6 +71,11 @@ class UserResponseModel_MLP(Environment):
                   for i, m in enumerate(self.mlp)]
         return ops.mlp_forward(segs, layers, B)["out"]
 
+
+    # pretrain_env.train_response_model sets `differentiable = True`: forward() then builds the autograd graph (embedding
+    # tables included).  Off by default: the generative path only ever scores slates with a frozen simulator, and the
+    # fused inference block is the one that is bit-identical to the oracle.
+    differentiable = False
 
     def _forward_train(self, slates, users):
         """Differentiable path (pretrain_env.py:76-88 trains the embeddings too): gather + normalise with a backward,

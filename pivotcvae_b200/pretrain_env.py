@@ -36,6 +36,7 @@ def train_response_model(trainset, valset, f_size, s_size, struct, bs, epochs, l
         logger.log("\t%s: %s" % (k, v))
     model = UserResponseModel_MLP(trainset.max_iid, trainset.max_uid, f_size, s_size, struct, device, trainset.noUser)
     model.to(device)
+    model.differentiable = True       # forward() builds the autograd graph, embedding tables included
     trainLoader = DataLoader(trainset, batch_size=bs, shuffle=True, num_workers=0)
     valLoader = DataLoader(valset, batch_size=bs, shuffle=False, num_workers=0)
     optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=decay)

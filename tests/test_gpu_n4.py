@@ -24,6 +24,7 @@ def test_response_pretrain_step(golden, tag, no_user, engine):
     n_items, n_users, Ls, D, B = [int(v) for v in fx["cfg"]]
     m = UserResponseModel_MLP(n_items - 1, n_users - 1, D, Ls, [(Ls if no_user else Ls + 1) * D, 64, 32, Ls], "cuda:0", no_user).to("cuda:0")
     load_sd(m, fx.sub(tag + "/sd/"))
+    m.differentiable = True
     batch = {"slates": fx[tag + "/slates"], "users": fx[tag + "/users"], "responses": fx[tag + "/resp"]}
     ag.MLP_BWD_ENGINE = engine
     try:
