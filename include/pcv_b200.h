@@ -185,7 +185,7 @@ typedef struct {
 
 #define PCV_MAX_SEGMENTS 6
 #define PCV_MAX_LAYERS 8
-#define PCV_MAX_WIDTH 512 /* widest layer / input supported */
+#define PCV_MAX_WIDTH 1024 /* widest layer / input supported (hyperparams.py:22,79,91 use 1024-wide response MLPs) */
 
 typedef struct {
   int n_segments;
@@ -359,6 +359,10 @@ int pcv_gather_norm_fwd(const float *doc, const float *usr, const int64_t *slate
 /* d_doc / d_usr (zero-initialised by the caller, same shapes as the tables) += the gradient of x0 w.r.t. the raw rows. */
 int pcv_gather_norm_bwd(const float *g, int64_t ldg, const float *x0, int64_t ld, const float *inv_norm, const int64_t *slates,
                         const int64_t *users, int64_t B, int L, int D, float *d_doc, float *d_usr, pcv_stream_t stream);
+/* Backward of the reparameterisation (cvae.py:79-83) folded into the gradient of a block's [mu | logvar] output
+ * (out: [B, ld_out] the block's saved output, columns 0..2Z-1; d_out / d_z may be NULL): g [B, 2Z] contiguous. */
+int pcv_reparam_bwd(const float *d_out, int64_t ld_dout, const float *d_z, const float *eps, const float *out, int64_t ld_out,
+                    int64_t B, int Z, float *g, pcv_stream_t stream);
 /* nn.BCELoss()(sigmoid(pred), target) (pretrain_env.py:57-58,84; logs clamped at -100) and dpred (optional). */
 int pcv_bce_sigmoid(const float *pred, const float *target, int64_t n, float *loss, float *dpred, pcv_stream_t stream);
 

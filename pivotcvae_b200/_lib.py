@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libpcv_b200.so")
 
 PCV_MAX_SEGMENTS = 6
 PCV_MAX_LAYERS = 8
-PCV_MAX_WIDTH = 512
+PCV_MAX_WIDTH = 1024
 
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 SEG_DENSE, SEG_ONEHOT, SEG_GATHER = 0, 1, 2
@@ -106,6 +106,7 @@ EXPORTS = {
     "pcv_gather_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "pcv_gather_norm_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
+    "pcv_reparam_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "pcv_bce_sigmoid": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pcv_kl_fwd_bwd": (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 5 + [c_void_p]),
     "pcv_ce_workspace_bytes": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_size_t)]),

@@ -126,6 +126,7 @@ class FusedMLPFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, B, n_dense, *tensors):
+        ctx.set_materialize_grads(False)      # an unused output (out or z) arrives as None, not as a zero-filled tensor
         dense = tensors[:n_dense]
         wb = tensors[n_dense:]
         layers = [(wb[2 * i], wb[2 * i + 1], spec.acts[i]) for i in range(len(wb) // 2)]
@@ -159,15 +160,20 @@ class FusedMLPFn(torch.autograd.Function):
         Ws = saved[nl + 1:nl + 1 + nl]
         c0 = spec.out_col0
         g = None
-        if d_out is not None:
-            g = d_out[:, c0:c0 + ctx.n_out]
-        if spec.latent:
-            Z = spec.latent
-            if d_z is not None:
-                eps = saved[-1]
-                std = torch.exp(0.5 * out[:, c0 + Z:c0 + 2 * Z])
-                gz = torch.cat([d_z, d_z * eps * 0.5 * std], 1)
-                g = gz if g is None else g + gz
+        if spec.latent and (d_z is not None) and c0 == 0 and ctx.n_out == 2 * spec.latent and MLP_BWD_ENGINE != "torch":
+            # [mu | logvar] block: the reparameterisation's backward and the sum with d_out in ONE kernel
+            do = d_out if (d_out is None or d_out.stride(1) == 1) else d_out.contiguous()
+            g = ops.reparam_bwd(do, d_z, saved[-1], out, spec.latent)
+        else:
+            if d_out is not None:
+                g = d_out[:, c0:c0 + ctx.n_out]
+            if spec.latent:
+                Z = spec.latent
+                if d_z is not None:
+                    eps = saved[-1]
+                    std = torch.exp(0.5 * out[:, c0 + Z:c0 + 2 * Z])
+                    gz = torch.cat([d_z, d_z * eps * 0.5 * std], 1)
+                    g = gz if g is None else g + gz
         if g is None:
             return (None,) * (3 + ctx.n_dense + 2 * nl)
         g = g.contiguous()
@@ -198,6 +204,7 @@ class CatalogCEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, table, targets, keep_prob, bitmask, seed, offset, offset_dev=None, engine="exact"):
+        ctx.set_materialize_grads(False)
         loss_rows, lse, dq = ops.ce_fwd_bwd(table, q, targets, keep_prob, bitmask, seed, offset,
                                             want_dq=q.requires_grad, offset_dev=offset_dev, engine=engine)
         ctx.M = q.shape[0]
@@ -209,10 +216,9 @@ class CatalogCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mean, g_rows, _g_lse):
         (dq,) = ctx.saved_tensors
-        scale = g_mean / ctx.M
-        d = dq * scale
+        d = dq * (g_mean / ctx.M) if g_mean is not None else None
         if g_rows is not None:
-            d = d + dq * g_rows.unsqueeze(1)
+            d = dq * g_rows.unsqueeze(1) if d is None else d + dq * g_rows.unsqueeze(1)
         return d, None, None, None, None, None, None, None, None
 
 
@@ -224,6 +230,7 @@ class VocabParallelCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, shard, full_weight, targets, group, engine="exact"):
         import torch.distributed as dist
+        ctx.set_materialize_grads(False)
         rec = ops.ce_partials(shard, q, targets, engine=engine)
         world = dist.get_world_size(group)
         recs = torch.empty(world * rec.shape[0], rec.shape[1], dtype=rec.dtype, device=rec.device)
@@ -239,9 +246,9 @@ class VocabParallelCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mean, g_rows, _g_lse):
         (dq,) = ctx.saved_tensors
-        d = dq * (g_mean / ctx.M)
+        d = dq * (g_mean / ctx.M) if g_mean is not None else None
         if g_rows is not None:
-            d = d + dq * g_rows.unsqueeze(1)
+            d = dq * g_rows.unsqueeze(1) if d is None else d + dq * g_rows.unsqueeze(1)
         return d, None, None, None, None, None
 
 
@@ -291,7 +298,7 @@ class KLFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go):
-        return tuple(go * g for g in ctx.saved_tensors)
+        return tuple(torch._foreach_mul(list(ctx.saved_tensors), go))      # one multi-tensor launch for the four gradients
 
 
 class LogitsFn(torch.autograd.Function):

@@ -50,6 +50,7 @@ static int ce_rows_for(int D) {
     case 16: return CECfg<16>::ROWS;
     case 32: return CECfg<32>::ROWS;
     case 64: return CECfg<64>::ROWS;
+    case 128: return CECfg<128>::ROWS;
   }
   return 0;
 }
@@ -81,7 +82,7 @@ __device__ __forceinline__ void ce_cp_async16(void *smem, const void *gmem, bool
 }
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(CE_THREADS, 2)
+__global__ void __launch_bounds__(CE_THREADS, (D <= 64 ? 2 : 1))
 ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
           const float *__restrict__ Q, const int64_t *__restrict__ targets, int64_t M,
           int64_t items_per_split, const uint32_t *__restrict__ bitmask, int64_t mask_words,
@@ -214,66 +215,104 @@ ce_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
   }
 }
 
-// One thread per row: merge split partials, add the masked-out mass, emit
-// loss / lse / dq.  Target logit re-derived with the exact FMA chain.
-__global__ void ce_finalize_kernel(const float *__restrict__ part, int n_split, int64_t M, int D,
-                                   const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
-                                   const float *__restrict__ Q, const int64_t *__restrict__ targets,
-                                   float *__restrict__ loss_rows, float *__restrict__ lse_out,
-                                   float *__restrict__ dq, float *__restrict__ rec_out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per row: lanes walk the row's partial records (lane = record, 32 at a time), each record's weight
+// e^{m - M} is computed once, and the max / sums are warp reductions in a fixed order (deterministic).  Adds the
+// masked-out mass, emits loss / lse / dq; the target logit is re-derived with the exact FMA chain.
+// rec_out != NULL (vocab-parallel shard): hand out the merged partial {m, l, acc[D]} of this shard's columns
+// instead (no target terms); pcv_ce_vp_merge combines the shards' records after the all-gather.
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const float *__restrict__ part, int n_split, int64_t M, int D,
+                   const float *__restrict__ W, int64_t n_rows, int64_t row_offset,
+                   const float *__restrict__ Q, const int64_t *__restrict__ targets,
+                   float *__restrict__ loss_rows, float *__restrict__ lse_out,
+                   float *__restrict__ dq, float *__restrict__ rec_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= M) return;
   const int REC = 3 + D;
   float mx = -INFINITY;
-  int64_t cnt = 0;
-  for (int s = 0; s < n_split; ++s) {
+  int cnt_l = 0;
+  for (int s = lane; s < n_split; s += 32) {
     const float *rec = part + ((int64_t)s * M + i) * REC;
     mx = fmaxf(mx, rec[0]);
-    cnt += __float_as_int(rec[2]);
+    cnt_l += __float_as_int(rec[2]);
   }
-  const int64_t n_out = n_rows - cnt;  // masked-out logits are exactly 0
+  mx = warp_max(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt_l += __shfl_xor_sync(0xffffffffu, cnt_l, o);
+  const int64_t n_out = n_rows - cnt_l;  // masked-out logits are exactly 0
   if (n_out > 0) mx = fmaxf(mx, 0.f);
-  float L = 0.f;
-  for (int s = 0; s < n_split; ++s) {
-    const float *rec = part + ((int64_t)s * M + i) * REC;
-    if (rec[0] != -INFINITY) L += rec[1] * __expf(rec[0] - mx);
+  // lane accumulates the dq components k = lane, lane + 32, lane + 64, lane + 96 (D <= 128); every lane needs every record's weight:
+  // records are processed in groups of 32 (lane = record), the group's weights are broadcast with shuffles
+  float L = 0.f, acc = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+  if (D <= 16) {
+    // small D (every BASELINE config: D = 8): lane = record keeps its own D scaled components (all loads independent,
+    // one round trip), then D warp sums; lane k ends up holding component k
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+    for (int s = lane; s < n_split; s += 32) {
+      const float *rec = part + ((int64_t)s * M + i) * REC;
+      if (rec[0] != -INFINITY) {
+        const float wgt = __expf(rec[0] - mx);
+        L += rec[1] * wgt;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < D) a[k] = fmaf(rec[3 + k], wgt, a[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float t = warp_sum(a[k]);
+      if (lane == k) acc = t;
+    }
+  } else
+  for (int base = 0; base < n_split; base += 32) {
+    const int s = base + lane;
+    float wgt = 0.f, l_s = 0.f;
+    const float *rec = part + ((int64_t)min(s, n_split - 1) * M + i) * REC;
+    if (s < n_split && rec[0] != -INFINITY) {
+      wgt = __expf(rec[0] - mx);
+      l_s = rec[1];
+    }
+    L += l_s * wgt;
+    const int n_here = min(32, n_split - base);
+    for (int j = 0; j < n_here; ++j) {
+      const float wj = __shfl_sync(0xffffffffu, wgt, j);
+      if (wj != 0.f) {
+        const float *rj = part + ((int64_t)(base + j) * M + i) * REC + 3;
+        if (lane < D) acc = fmaf(rj[lane], wj, acc);
+        if (lane + 32 < D) acc2 = fmaf(rj[lane + 32], wj, acc2);
+        if (lane + 64 < D) acc3 = fmaf(rj[lane + 64], wj, acc3);
+        if (lane + 96 < D) acc4 = fmaf(rj[lane + 96], wj, acc4);
+      }
+    }
   }
+  L = warp_sum(L);
   L += (float)n_out * __expf(-mx);
   if (rec_out) {
-    // vocab-parallel shard: hand out the merged partial {m, l, acc[D]} of this shard's columns (no target terms);
-    // pcv_ce_vp_merge combines the shards' records after the all-gather
     float *o = rec_out + i * (2 + D);
-    o[0] = mx;
-    o[1] = L;
-    for (int k = 0; k < D; ++k) {
-      float a = 0.f;
-      for (int s = 0; s < n_split; ++s) {
-        const float *rec = part + ((int64_t)s * M + i) * REC;
-        if (rec[0] != -INFINITY) a += rec[3 + k] * __expf(rec[0] - mx);
-      }
-      o[2 + k] = a;
-    }
+    if (lane == 0) { o[0] = mx; o[1] = L; }
+    if (lane < D) o[2 + lane] = acc;
+    if (lane + 32 < D) o[2 + lane + 32] = acc2;
+    if (lane + 64 < D) o[2 + lane + 64] = acc3;
+    if (lane + 96 < D) o[2 + lane + 96] = acc4;
     return;
   }
   const float lse = mx + logf(L);
   const int64_t t = targets[i] - row_offset;
   const float *wt = W + t * D;
   const float *qi = Q + i * D;
-  float xt = 0.f;
-  for (int k = 0; k < D; ++k) xt = fmaf(qi[k], wt[k], xt);
-  if (loss_rows) loss_rows[i] = lse - xt;
-  if (lse_out) lse_out[i] = lse;
-  if (dq) {
-    const float inv = 1.f / L;
-    for (int k = 0; k < D; ++k) {
-      float a = 0.f;
-      for (int s = 0; s < n_split; ++s) {
-        const float *rec = part + ((int64_t)s * M + i) * REC;
-        if (rec[0] != -INFINITY) a += rec[3 + k] * __expf(rec[0] - mx);
-      }
-      dq[i * D + k] = a * inv - wt[k];
-    }
+  if (lane == 0) {
+    float xt = 0.f;
+    for (int k = 0; k < D; ++k) xt = fmaf(qi[k], wt[k], xt);
+    if (loss_rows) loss_rows[i] = lse - xt;
+    if (lse_out) lse_out[i] = lse;
   }
+  if (dq && lane < D) dq[i * D + lane] = acc * (1.f / L) - wt[lane];
+  if (dq && lane + 32 < D) dq[i * D + lane + 32] = acc2 * (1.f / L) - wt[lane + 32];
+  if (dq && lane + 64 < D) dq[i * D + lane + 64] = acc3 * (1.f / L) - wt[lane + 64];
+  if (dq && lane + 96 < D) dq[i * D + lane + 96] = acc4 * (1.f / L) - wt[lane + 96];
 }
 
 // Vocab-parallel merge: recs = [G][M][2 + D] shard records {m, l, acc[D]} in any shard order
@@ -559,8 +598,9 @@ static int ce_dispatch(const Table *t, const CEPlan &p, const float *Q, const in
     case 16: return launch_ce<16, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
     case 32: return launch_ce<32, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
     case 64: return launch_ce<64, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
+    case 128: return launch_ce<128, MODE>(t, p, Q, targets, M, bitmask, mask_words, seed, offset, offset_dev, thresh, part, st);
   }
-  set_error("ce: dim %d unsupported (use 4, 8, 16, 32 or 64)", t->dim);
+  set_error("ce: dim %d unsupported (use 4, 8, 16, 32, 64 or 128)", t->dim);
   return PCV_ERR_UNSUPPORTED;
 }
 
@@ -592,6 +632,7 @@ int pcv_cand_ce_fwd_bwd(const pcv_table *th, const float *Q, const int64_t *cand
     case 16: cand_ce_kernel<16><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
     case 32: cand_ce_kernel<32><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
     case 64: cand_ce_kernel<64><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
+    case 128: cand_ce_kernel<128><<<blocks, 256, 0, st>>>(t->W, Q, candidates, target_pos, M, n_cand, loss_rows, lse, dq, logits_out); break;
     default:
       set_error("cand_ce: dim %d unsupported", t->dim);
       return PCV_ERR_UNSUPPORTED;
@@ -652,7 +693,7 @@ static int ce_run(const pcv_table *th, const float *Q, const int64_t *targets, i
     }
     const int n_parts = ce_tc_launch(t, Q, targets, M, part, workspace_bytes, st);
     if (n_parts < 0) return n_parts;
-    ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(part, n_parts, M, t->dim, t->W, t->n_rows,
+    ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(part, n_parts, M, t->dim, t->W, t->n_rows,
                                                                     t->row_offset, Q, targets, loss_rows, lse, dq, rec_out);
     PCV_LAUNCH_CHECK();
     return PCV_OK;
@@ -667,12 +708,13 @@ static int ce_run(const pcv_table *th, const float *Q, const int64_t *targets, i
       case 16: return launch_ce_sparse<16>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
       case 32: return launch_ce_sparse<32>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
       case 64: return launch_ce_sparse<64>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
+      case 128: return launch_ce_sparse<128>(t, Q, targets, M, mask, T, loss_rows, lse, dq, st);
     }
     set_error("ce: dim %d unsupported", t->dim);
     return PCV_ERR_UNSUPPORTED;
   }
   if (rc != PCV_OK) return rc;
-  ce_finalize_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(
+  ce_finalize_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(
       part, p.n_split, M, t->dim, t->W, t->n_rows, t->row_offset, Q, targets, loss_rows, lse, dq, rec_out);
   PCV_LAUNCH_CHECK();
   return PCV_OK;

@@ -786,10 +786,16 @@ static int mlp_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaS
     if (rc != PCV_OK || done) return rc;
   }
   // rows per CTA: 8 / 16 / 32 — small batches spread over more SMs (and use 16 warps per CTA)
-  const int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
-  const int BM = 8 * CT;
+  int CT = (B <= (int64_t)sm_count * 16) ? 1 : (B <= (int64_t)sm_count * 64 ? 2 : 4);
   const int ld = Pb ? (Pa->ld > Pb->ld ? Pa->ld : Pb->ld) : Pa->ld;
-  size_t smem = (size_t)(2 * ld * (BM + 4) + 2 * MLP_KC * MLP_WLD_MAX) * sizeof(float);
+  auto smem_of = [&](int ct) { return (size_t)(2 * ld * (8 * ct + 4) + 2 * MLP_KC * MLP_WLD_MAX) * sizeof(float); };
+  while (CT > 1 && smem_of(CT) > 227 * 1024) CT >>= 1;   // wide layers (up to PCV_MAX_WIDTH = 1024): fewer rows per CTA
+  const int BM = 8 * CT;
+  size_t smem = smem_of(CT);
+  if (smem > 227 * 1024) {
+    set_error("pcv_mlp_fwd: activations of width %d do not fit shared memory", ld);
+    return PCV_ERR_UNSUPPORTED;
+  }
   int64_t blocks = (B + BM - 1) / BM;
 #define PCV_MLP_LAUNCH(CTv, RTv, THv)                                                                              \
   if (Pb) {                                                                                                        \

@@ -102,6 +102,24 @@ bce_sigmoid_kernel(const float *__restrict__ p, const float *__restrict__ t, int
   }
 }
 
+// Backward of the reparameterisation epilogue (cvae.py:79-83: z = eps * exp(0.5 logvar) + mu) folded into the gradient of
+// the block's [mu | logvar] output: g[b, j] = d_out[b, j] + d_z[b, j]            (j < Z)
+//                                 g[b, Z + j] = d_out[b, Z + j] + d_z[b, j] * eps[b, j] * 0.5 * exp(0.5 * logvar[b, j])
+__global__ void reparam_bwd_kernel(const float *__restrict__ d_out, int64_t ld_dout, const float *__restrict__ d_z,
+                                   const float *__restrict__ eps, const float *__restrict__ out, int64_t ld_out, int64_t B, int Z,
+                                   float *__restrict__ g) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B * 2 * Z) return;
+  const int64_t b = f / (2 * Z);
+  const int j = (int)(f % (2 * Z));
+  float v = d_out ? d_out[b * ld_dout + j] : 0.f;
+  if (d_z) {
+    if (j < Z) v += d_z[b * Z + j];
+    else v += d_z[b * Z + j - Z] * eps[b * Z + j - Z] * (0.5f * expf(0.5f * out[b * ld_out + j]));
+  }
+  g[f] = v;
+}
+
 }  // namespace pcv
 
 using namespace pcv;
@@ -129,6 +147,18 @@ int pcv_gather_norm_bwd(const float *g, int64_t ldg, const float *x0, int64_t ld
   if (rc != PCV_OK) return rc;
   gather_norm_bwd_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, ldg, x0, ld, inv_norm, slates, users, B, L, D,
                                                                                   d_doc, d_usr);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+int pcv_reparam_bwd(const float *d_out, int64_t ld_dout, const float *d_z, const float *eps, const float *out, int64_t ld_out,
+                    int64_t B, int Z, float *g, pcv_stream_t stream) {
+  PCV_CHECK_ARG(g && out && B > 0 && Z > 0, "bad arguments");
+  PCV_CHECK_ARG(d_z == nullptr || eps != nullptr, "d_z needs eps");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  const int64_t n = B * 2 * Z;
+  reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, ld_dout, d_z, eps, out, ld_out, B, Z, g);
   PCV_LAUNCH_CHECK();
   return PCV_OK;
 }

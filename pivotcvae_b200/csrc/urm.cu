@@ -160,8 +160,10 @@ int pcv_slate_metrics(const float *table, int D, const int64_t *slates, int64_t 
     case 8: slate_metrics_kernel<8><<<blocks, 128, 0, st>>>(table, slates, B, L, ils, bitmap); break;
     case 16: slate_metrics_kernel<16><<<blocks, 128, 0, st>>>(table, slates, B, L, ils, bitmap); break;
     case 32: slate_metrics_kernel<32><<<blocks, 128, 0, st>>>(table, slates, B, L, ils, bitmap); break;
+    case 64: slate_metrics_kernel<64><<<blocks, 128, 0, st>>>(table, slates, B, L, ils, bitmap); break;
+    case 128: slate_metrics_kernel<128><<<blocks, 128, 0, st>>>(table, slates, B, L, ils, bitmap); break;
     default:
-      set_error("pcv_slate_metrics: dim %d unsupported (use 4, 8, 16 or 32)", D);
+      set_error("pcv_slate_metrics: dim %d unsupported (use 4, 8, 16, 32, 64 or 128)", D);
       return PCV_ERR_UNSUPPORTED;
   }
   PCV_LAUNCH_CHECK();
@@ -197,8 +199,10 @@ int pcv_urm_fwd(const pcv_urm_desc *d, const int64_t *slates, const int64_t *use
     case 8: urm_kernel<8><<<blocks, 128, 0, st>>>(*d, slates, users, B, out); break;
     case 16: urm_kernel<16><<<blocks, 128, 0, st>>>(*d, slates, users, B, out); break;
     case 32: urm_kernel<32><<<blocks, 128, 0, st>>>(*d, slates, users, B, out); break;
+    case 64: urm_kernel<64><<<blocks, 128, 0, st>>>(*d, slates, users, B, out); break;
+    case 128: urm_kernel<128><<<blocks, 128, 0, st>>>(*d, slates, users, B, out); break;
     default:
-      set_error("pcv_urm_fwd: dim %d unsupported (use 4, 8, 16 or 32)", d->D);
+      set_error("pcv_urm_fwd: dim %d unsupported (use 4, 8, 16, 32, 64 or 128)", d->D);
       return PCV_ERR_UNSUPPORTED;
   }
   PCV_LAUNCH_CHECK();

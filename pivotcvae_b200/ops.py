@@ -649,6 +649,19 @@ def gather_norm_bwd(g, x0, inv, slates, users, doc_shape, usr_shape):
     return d_doc, d_usr
 
 
+def reparam_bwd(d_out, d_z, eps, out, Z):
+    """Gradient w.r.t. a block's [mu | logvar] output with the reparameterisation's backward folded in (one launch).
+    d_out: [B, >= 2Z] view or None, d_z: [B, Z] or None, out: the block's saved output (columns 0..2Z-1)."""
+    B = out.shape[0]
+    g = torch.empty(B, 2 * Z, dtype=torch.float32, device=out.device)
+    if d_z is not None:
+        d_z, eps = _f32(d_z, "d_z"), _f32(eps, "eps")
+    with torch.cuda.device(out.device):
+        L.check(L.load().pcv_reparam_bwd(_ptr(d_out), d_out.stride(0) if d_out is not None else 0, _ptr(d_z), _ptr(eps),
+                                         _ptr(out), out.stride(0), B, int(Z), _ptr(g), _stream()), "pcv_reparam_bwd")
+    return g
+
+
 def bce_sigmoid(pred, target, want_grad=True):
     """nn.BCELoss()(sigmoid(pred), target) -> (loss scalar tensor, dpred | None)."""
     pred, target = _f32(pred, "pred").reshape(-1), _f32(target, "target").reshape(-1)

@@ -250,7 +250,8 @@ def test_normalize_rows(ops):
 
 
 # ------------------------------------------------------------------ CE / KL
-@pytest.mark.parametrize("n_items,M,D", [(500, 37, 8), (5000, 130, 8), (40000, 64, 8), (3000, 50, 16), (1000, 33, 32)])
+@pytest.mark.parametrize("n_items,M,D", [(500, 37, 8), (5000, 130, 8), (40000, 64, 8), (3000, 50, 16), (1000, 33, 32),
+                                         (1500, 41, 64), (900, 19, 128)])      # --dim is free in the reference
 @pytest.mark.parametrize("mode", ["dense", "bitmask", "philox"])
 def test_ce_fwd_bwd(ops, n_items, M, D, mode):
     rng = np.random.default_rng(n_items + M)
@@ -369,3 +370,35 @@ def test_ce_vocab_parallel_partials_merge(ops, n_items, M, G, engine):
     # the torch restatement used by the gloo CPU test agrees with the kernel
     pl, ps, pd = merge_ce_partials(recs, Wt, Qt, tt)
     assert np.allclose(N(pl), N(loss), rtol=1e-5, atol=1e-5) and np.allclose(N(pd), N(dq), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("D", [16, 64, 128])
+def test_urm_metrics_and_candidate_ce_other_dims(ops, D):
+    """--dim other than 8 (train_generative.py:302 leaves it free): URM variants, slate metrics and the candidate CE
+    against the oracle restatements."""
+    from pivotcvae_b200 import _lib as L
+    from pivotcvae_b200 import analysis
+    rng = np.random.default_rng(D)
+    n_items, n_users, B, Ls = 700, 90, 257, 5
+    doc = rng.standard_normal((n_items, D)).astype(np.float32)
+    usr = rng.standard_normal((n_users, D)).astype(np.float32)
+    ib = (0.1 * rng.standard_normal(n_items)).astype(np.float32)
+    ub = (0.1 * rng.standard_normal(n_users)).astype(np.float32)
+    pb = rng.standard_normal(Ls).astype(np.float32)
+    pd = rng.standard_normal((Ls, D)).astype(np.float32)
+    slates = rng.integers(0, n_items, (B, Ls))
+    users = rng.integers(0, n_users, B)
+    got = ops.urm_forward(L.URM_P_MR, T(doc), T(usr), T(ib), T(ub), T(slates), T(users), pos_bias=T(pb), pos_dep=T(pd), mr_factor=0.3)
+    want = oracle.urm(L.URM_P_MR, doc, usr, ib, ub, slates, users, pos_bias=pb, pos_dep=pd, mr_factor=0.3)
+    np.testing.assert_allclose(N(got), want, rtol=1e-5, atol=1e-6)
+    ils, _ = analysis._metrics(T(slates), T(doc), True, False)
+    np.testing.assert_allclose(N(ils), oracle.ils(doc, slates), rtol=1e-4, atol=1e-6)
+    W = doc / np.linalg.norm(doc, axis=1, keepdims=True)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    cand = rng.integers(0, n_items, (B, 50))
+    tp = rng.integers(0, 50, B)
+    loss, lse, dq, p = ops.cand_ce_fwd_bwd(ops.Table(T(W)), T(Q), T(cand), T(tp), want_logits=True)
+    rl, rdq, rp = oracle.cand_ce(W, Q, cand, tp)
+    np.testing.assert_allclose(N(loss), rl, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N(dq), rdq, rtol=1e-3, atol=2e-6)
+    assert np.array_equal(N(p), rp)
