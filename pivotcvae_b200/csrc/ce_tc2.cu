@@ -19,7 +19,7 @@
 //   c = max(lb, ub - 60)   =>   s_j - c <= 60 (no overflow: e^60 * N << 3e38) and max_j s_j - c >= lb - ub + 60,
 // which cannot underflow when lb >= ub - 140.  Rows that fail that test (never seen in practice: it needs
 // |q| max|w| > 70 with a far-off target) are flagged and redone exactly by ce_rowfix_kernel (warp per row).
-// The per-(split, column slice) records (c, l, count, acc[8]) have the layout of ce.cu and are merged by the same
+// The per-(split, row) records (c, l, count, acc[8]) have the layout of ce.cu and are merged by the same
 // ce_finalize_kernel (target logit re-derived with the exact fp32 FMA chain).
 #include "tc_common.cuh"
 
@@ -31,7 +31,6 @@ constexpr int C2_DQ_COL = C2_BUFS * C2_BN;      // dq accumulators: C2_DQ_ACCS x
 constexpr int C2_DQ_ACCS = 4;                   // N = 16 gradient MMAs are 8 cycles of work each: four independent
                                                 // accumulators keep the tensor pipe from waiting on its own accumulate latency
 constexpr int C2_EPI_WARPS = 16;                // 4 per TMEM lane quarter, each a 32-column slice
-constexpr int C2_SLICES = C2_EPI_WARPS / 4;
 constexpr int C2_THREADS = 64 + 32 * C2_EPI_WARPS;
 constexpr int C2_STAGES = 12;
 constexpr int C2_W_FLOATS = C2_BN * 8;          // W tile: 128 rows x 32 B (SWIZZLE_32B image), 4 KB
@@ -44,6 +43,7 @@ struct __align__(1024) Ce2Smem {
   float a[2][TC_BM * 8];
   unsigned long long full[C2_STAGES], empty[C2_STAGES], tfull[C2_BUFS], pfull[C2_BUFS], tempty[C2_BUFS];
   unsigned long long afull[2], aempty[2], dqfull, dqempty;
+  float lsum[2][TC_BM];      // per-row sum of l over the column slices 1..3 of a work item (double-buffered by item parity)
   uint32_t tmem_base;
 };
 
@@ -196,6 +196,7 @@ ce_tc2_kernel(const float *__restrict__ Wsw, const float *__restrict__ Wt, int64
   const int hw_warp = threadIdx.x >> 5;
   const int warp = hw_warp >= C2_EPI_WARPS ? hw_warp - C2_EPI_WARPS : hw_warp + 2;
 
+  if (threadIdx.x < 2 * TC_BM) (&S.lsum[0][0])[threadIdx.x] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C2_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     for (int b = 0; b < C2_BUFS; ++b) {
@@ -399,15 +400,24 @@ ce_tc2_kernel(const float *__restrict__ Wsw, const float *__restrict__ Wt, int64
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.dqempty);
       }
-      if (row < M) {
-        const int64_t stream = (int64_t)item_split(w) * C2_SLICES + slice;
-        float *rec = part + (stream * M + row) * C2_REC;
-        rec[0] = (cnt > 0) ? __ldg(cref + row) : -INFINITY;
-        rec[1] = l;
-        rec[2] = __int_as_float(cnt);
+      // ONE record per (split, row): the other three column slices add their l into shared memory, a named barrier
+      // over the four warps of this TMEM lane quarter orders it, the slice-0 warp writes the record
+      float *ls = &S.lsum[it & 1][trow];
+      if (slice != 0) atomicAdd(ls, l);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      if (slice == 0) {
+        l += *ls;
+        *ls = 0.f;             // this buffer is used again two items later, behind the next item's barrier
+        if (row < M) {
+          float *rec = part + ((int64_t)item_split(w) * M + row) * C2_REC;
+          rec[0] = __ldg(cref + row);
+          rec[1] = l;
+          rec[2] = __int_as_float((int)(j_end - j_begin));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) rec[3 + k] = acc[k];
+          for (int k = 0; k < 8; ++k) rec[3 + k] = acc[k];
+        }
       }
+      (void)cnt;
     }
   }
 
@@ -445,7 +455,7 @@ static void ce2_plan(const Table *t, int64_t M, Ce2Plan *p) {
   const int64_t tps = (tiles + best_ns - 1) / best_ns;
   p->n_split = (int)((tiles + tps - 1) / tps);
   p->items_per_split = tps * C2_BN;
-  p->rec_bytes = ((size_t)p->n_split * C2_SLICES * (size_t)M * C2_REC * sizeof(float) + 255) & ~(size_t)255;
+  p->rec_bytes = ((size_t)p->n_split * (size_t)M * C2_REC * sizeof(float) + 255) & ~(size_t)255;   // one record per (split, row)
   p->ws_bytes = p->rec_bytes + (((size_t)M * 4 + 255) & ~(size_t)255) + (((size_t)M + 255) & ~(size_t)255);
 }
 
@@ -513,7 +523,7 @@ int ce_tc_launch(const Table *tc, const float *Q, const int64_t *targets, int64_
   }
   float *cref = reinterpret_cast<float *>(reinterpret_cast<char *>(part) + p.rec_bytes);
   unsigned char *unsafe = reinterpret_cast<unsigned char *>(cref) + (((size_t)M * 4 + 255) & ~(size_t)255);
-  const int n_streams = p.n_split * C2_SLICES;
+  const int n_streams = p.n_split;
   ce_ref_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, t->max_row_norm, Q, targets, M, cref, unsafe);
   PCV_LAUNCH_CHECK();
   const size_t smem = sizeof(Ce2Smem) + 1024;
