@@ -286,8 +286,11 @@ typedef struct {
   const uint32_t *bitmask; /* parity mode: [M, ceil(N/32)] bit j%32 of word j/32 = Bernoulli draw (target is OR-ed in by the kernel) */
   uint64_t seed, offset;   /* Philox mode (bitmask == NULL && keep_prob < 1)         */
   const uint64_t *offset_dev; /* optional device counter added to `offset` (CUDA-graph replays) */
-  int engine;              /* PCV_CE_ENGINE_*: EXACT (default) or TF32 (dense mask, dim 8: logits on the
-                              tensor cores, loss ~1e-4 / dq ~1e-3 relative — the reduced-precision tolerance) */
+  int engine;              /* PCV_CE_ENGINE_*: EXACT (default) or TF32 (dense mask, dim 8: logits AND the gradient
+                              contraction on the tensor cores, loss ~1e-4 / dq ~1e-3 relative — the reduced-precision
+                              tolerance).  The first TF32 call on a table handle builds its transposed tile image
+                              (one-off allocation + device sync, like pcv_table_create): run it once outside any
+                              CUDA-graph capture */
 } pcv_ce_mask;
 #define PCV_CE_ENGINE_EXACT 0
 #define PCV_CE_ENGINE_TF32 1
