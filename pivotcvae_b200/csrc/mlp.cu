@@ -410,6 +410,7 @@ __device__ __forceinline__ void st_cluster_f1(uint32_t local_addr, uint32_t rank
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
+template <int ST>
 __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float *actA, float *actB, const float *stage,
                                            unsigned long long *full, unsigned long long *empty, uint32_t &g,
                                            uint32_t crank) {
@@ -443,8 +444,8 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
 #pragma unroll
           for (int c = 0; c < CT; ++c) acc2[r][c] = 0ull;
         for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
-          const int s = g % MLPC_STAGES;
-          mbar_wait(&full[s], (g / MLPC_STAGES) & 1);
+          const int s = g % ST;
+          mbar_wait(&full[s], (g / ST) & 1);
           if (active) {
             const float *ws = stage + (size_t)s * MLPC_TILE_FLOATS + lane * CT;
             const float *ap = cur + (size_t)kc * MLPC_ALD + wrp * RT;
@@ -524,8 +525,8 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
         const bool two = nbw > 32;
         float acc0 = 0.f, acc1 = 0.f;
         for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
-          const int s = g % MLPC_STAGES;
-          mbar_wait(&full[s], (g / MLPC_STAGES) & 1);
+          const int s = g % ST;
+          mbar_wait(&full[s], (g / ST) & 1);
           const float *ws = stage + (size_t)s * MLPC_TILE_FLOATS + lane;
           const float *ap = cur + (size_t)kc * MLPC_ALD + row;
           if (two) {
@@ -570,18 +571,21 @@ __device__ __forceinline__ void mlpc_block(const MlpParams &P, int64_t B, float 
 
 // warps 0-7 compute; warp 8 streams this CTA's weight tiles of the whole launch (both blocks of a
 // chain back to back: the second block's weights prefetch while the first one finishes)
+// ST = stages of the weight ring: 8 (64 KB, deepest prefetch) when the launch is a single wave, 4 (32 KB) when there
+// are more CTAs than SMs, so that TWO CTAs fit an SM (2 x ~107 KB) and one hides the other's barrier / TMA latencies
+template <int ST>
 __global__ void __cluster_dims__(MLPC_CL, 1, 1) __launch_bounds__(MLPC_NC + 32)
 mlp_cluster_kernel(const MlpParams2 P, int n_blocks, int64_t B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *stage = reinterpret_cast<float *>(smem_raw);                               // [8][32][64]
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(stage + MLPC_STAGES * MLPC_TILE_FLOATS);
-  unsigned long long *empty = full + MLPC_STAGES;
-  float *actA = reinterpret_cast<float *>(empty + MLPC_STAGES);                      // 16-byte aligned
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(stage + ST * MLPC_TILE_FLOATS);
+  unsigned long long *empty = full + ST;
+  float *actA = reinterpret_cast<float *>(empty + ST);                      // 16-byte aligned
   float *actB = actA + (size_t)P.a.ld * MLPC_ALD;
   const uint32_t crank = cluster_rank();
   MLP_TRACE(0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MLPC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MLPC_NC / 32); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MLPC_NC / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -635,8 +639,8 @@ mlp_cluster_kernel(const MlpParams2 P, int n_blocks, int64_t B) {
             const float *src = d.layer[l].Wp + (int64_t)nb * kpad;
             const uint32_t bytes = (uint32_t)(MLP_KC * nbw * sizeof(float));
             for (int kc = 0; kc < K; kc += MLP_KC, ++g) {
-              const int s = g % MLPC_STAGES;
-              mbar_wait(&empty[s], ((g / MLPC_STAGES) & 1) ^ 1);
+              const int s = g % ST;
+              mbar_wait(&empty[s], ((g / ST) & 1) ^ 1);
               mbar_expect_tx(&full[s], bytes);
               tma_bulk_load(stage + (size_t)s * MLPC_TILE_FLOATS, src + (int64_t)kc * nbw, bytes, &full[s]);
             }
@@ -649,13 +653,13 @@ mlp_cluster_kernel(const MlpParams2 P, int n_blocks, int64_t B) {
     return;
   }
   uint32_t g = 0;
-  mlpc_block(P.a, B, actA, actB, stage, full, empty, g, crank);
+  mlpc_block<ST>(P.a, B, actA, actB, stage, full, empty, g, crank);
   MLP_TRACE(20);
   if (n_blocks > 1) {
     // block B's prologue reads what rank 0 just wrote to HBM for the cluster's batch rows (z)
     __threadfence();
     cluster_sync_all();
-    mlpc_block(P.b, B, actA, actB, stage, full, empty, g, crank);
+    mlpc_block<ST>(P.b, B, actA, actB, stage, full, empty, g, crank);
   }
 }
 
@@ -759,16 +763,25 @@ static bool mlp_all_packed(const MlpParams *P) {
 static int mlp_launch_cluster(const MlpParams *Pa, const MlpParams *Pb, int64_t B, int ld, cudaStream_t st, bool *done) {
   *done = false;
   ld = (ld + MLP_KC - 1) / MLP_KC * MLP_KC;   // k ranges / column blocks are zero-padded to multiples of 32
-  const size_t smem = (size_t)MLPC_STAGES * MLPC_TILE_FLOATS * sizeof(float) + 2 * MLPC_STAGES * 8 +
+  const int64_t clusters = (B + MLPC_BM - 1) / MLPC_BM;
+  int sm_count = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int stages = (clusters * MLPC_CL > sm_count) ? 4 : MLPC_STAGES;
+  const size_t smem = (size_t)stages * MLPC_TILE_FLOATS * sizeof(float) + 2 * stages * 8 +
                       (size_t)2 * ld * MLPC_ALD * sizeof(float);
   if (smem > 227 * 1024) return PCV_OK;   // does not fit: the caller falls back to the streaming engine
-  const int64_t clusters = (B + MLPC_BM - 1) / MLPC_BM;
   MlpParams2 P2;
   P2.a = *Pa;
   P2.b = Pb ? *Pb : *Pa;
   P2.a.ld = ld; P2.b.ld = ld;
-  PCV_CUDA(cudaFuncSetAttribute(mlp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mlp_cluster_kernel<<<(unsigned)(clusters * MLPC_CL), MLPC_NC + 32, smem, st>>>(P2, Pb ? 2 : 1, B);
+  if (stages == 4) {
+    PCV_CUDA(cudaFuncSetAttribute(mlp_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_cluster_kernel<4><<<(unsigned)(clusters * MLPC_CL), MLPC_NC + 32, smem, st>>>(P2, Pb ? 2 : 1, B);
+  } else {
+    PCV_CUDA(cudaFuncSetAttribute(mlp_cluster_kernel<MLPC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_cluster_kernel<MLPC_STAGES><<<(unsigned)(clusters * MLPC_CL), MLPC_NC + 32, smem, st>>>(P2, Pb ? 2 : 1, B);
+  }
   PCV_LAUNCH_CHECK();
   *done = true;
   return PCV_OK;
