@@ -48,6 +48,16 @@ class MlpSpec:
 MLP_BWD_ENGINE = "tc3"
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+    n = _SM_COUNT.get(device)
+    if n is None:
+        n = _SM_COUNT[device] = torch.cuda.get_device_properties(device).multi_processor_count
+    return n
+
+
 def _padded(rows, cols, like):
     """[rows, cols] view of a fresh buffer whose leading dimension is a multiple of 4 floats (TMA operand rule)."""
     return torch.empty(rows, ops.pad4(cols), dtype=torch.float32, device=like.device)
@@ -91,7 +101,7 @@ def _mlp_backward_tc(g, x0, acts, Ws, act_ids, need_input_grad, split3):
     for l in range(nl - 1, -1, -1):
         n_out, n_in = Ws[l].shape
         tiles = -(-n_out // 128) * -(-n_in // 128)
-        splits = max(1, min(-(-B // 128), 148 // tiles, 32))
+        splits = max(1, min(-(-B // 128), _sm_count(g.device) // tiles, 32))     # ~one CTA per SM, >= 128 batch rows per slice
         part = torch.empty(splits, n_out, ops.pad4(n_in), dtype=torch.float32, device=g.device)
         ops.gemm_tn(gt, XT[l], n_out, n_in, B, A_lo=gt_lo, B_lo=XTlo[l], C=part, split_k=splits)
         dW = torch.empty(n_out, n_in, dtype=torch.float32, device=g.device)

@@ -21,6 +21,8 @@
 // |q| max|w| > 70 with a far-off target) are flagged and redone exactly by ce_rowfix_kernel (warp per row).
 // The per-(split, row) records (c, l, count, acc[8]) have the layout of ce.cu and are merged by the same
 // ce_finalize_kernel (target logit re-derived with the exact fp32 FMA chain).
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace pcv {
@@ -470,6 +472,8 @@ size_t ce_tc_workspace(const Table *t, int64_t M) {
 
 // The transposed image is built on first use (one-off, like the table handle's other packed copy) and owned by it.
 static int ensure_packed_t(Table *t) {
+  static std::mutex mu;                 // two host threads may hit the first tensor-core CE call of a handle together
+  std::lock_guard<std::mutex> lock(mu);
   if (t->packed_t) return PCV_OK;
   const int64_t tiles = (t->n_rows + C2_BN - 1) / C2_BN;
   const size_t bytes = (size_t)tiles * C2_WT_FLOATS * sizeof(float);

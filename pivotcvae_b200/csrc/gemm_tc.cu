@@ -26,6 +26,7 @@
 namespace pcv {
 
 constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 32;   // 32 fp32 = one 128-byte swizzle row
+static_assert(GM_BM == GM_BN, "one tensor-map box shape (32 floats x 128 rows) serves both operands");
 constexpr int GM_MAX_STAGES = 4;
 constexpr int GM_THREADS = 192;
 constexpr uint32_t GM_TILE_BYTES = GM_BM * GM_BK * 4;   // 16 KB per operand tile
