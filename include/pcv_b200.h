@@ -165,6 +165,11 @@ typedef struct {
    * of a launch carries one, the TMA engine runs (one bulk copy per 32-k chunk, FMA-pipe-bound);
    * results are bit-identical.  The caller re-packs after the weights change. */
   const float *Wp;
+  /* optional: the same weights split in tf32 hi | lo and pre-swizzled by pcv_mlp_tc_pack.  When EVERY layer of a
+   * launch carries one (and the block fits: assembled input <= 64 wide, layers <= 256 wide, no saved activations) the
+   * tensor-core engine runs (csrc/mlp_tc.cu: tcgen05 3xTF32, activations chained through TMEM).  fp32-grade results
+   * (~1e-6 relative of torch's addmm) but NOT bit-identical to the FFMA engines. */
+  const float *Wt;
 } pcv_linear;
 
 #define PCV_SEG_DENSE 0  /* ptr: float[B, width]                                      */
@@ -222,6 +227,10 @@ int pcv_mlp_fwd2(const pcv_mlp_desc *a, const pcv_mlp_desc *b, int64_t B, pcv_st
  * holds pcv_mlp_packed_bytes(n_in, n_out) bytes. */
 size_t pcv_mlp_packed_bytes(int n_in, int n_out);
 int pcv_mlp_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream);
+/* The tensor-core engine's image of one nn.Linear weight (pcv_linear.Wt): per 32-k chunk the [n_out_pad16][32] tf32-hi
+ * and tf32-lo matrices in the K-major SWIZZLE_128B shared-memory layout, so a chunk is one TMA bulk copy. */
+size_t pcv_mlp_tc_packed_bytes(int n_in, int n_out);
+int pcv_mlp_tc_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream);
 
 /* ------------------------------------------------------------------ */
 /* Tensor-core GEMMs of the MLP blocks' backward (and forward Linear)  */

@@ -36,7 +36,7 @@ class SelectOpts(ctypes.Structure):
 
 class Linear(ctypes.Structure):
     _fields_ = [("W", c_void_p), ("b", c_void_p), ("n_in", c_int), ("n_out", c_int), ("act", c_int),
-                ("Wp", c_void_p)]
+                ("Wp", c_void_p), ("Wt", c_void_p)]
 
 
 class Segment(ctypes.Structure):
@@ -120,6 +120,8 @@ EXPORTS = {
                                     c_void_p, c_void_p]),
     "pcv_mlp_packed_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "pcv_mlp_pack": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pcv_mlp_tc_packed_bytes": (ctypes.c_size_t, [c_int, c_int]),
+    "pcv_mlp_tc_pack": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pcv_slate_metrics": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pcv_popcount": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pcv_urm_fwd": (c_int, [ctypes.POINTER(UrmDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcv_b200.so")
 STAMP = os.path.join(HERE, "build", "sources.sha256")
 
-SOURCES = ["pcv_api.cu", "score_select.cu", "score_select_tc.cu", "mlp.cu", "ce.cu", "ce_tc2.cu", "urm.cu", "sampler.cu", "topk.cu", "gemm_tc.cu", "pretrain.cu"]
+SOURCES = ["pcv_api.cu", "score_select.cu", "score_select_tc.cu", "mlp.cu", "mlp_tc.cu", "ce.cu", "ce_tc2.cu", "urm.cu", "sampler.cu", "topk.cu", "gemm_tc.cu", "pretrain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

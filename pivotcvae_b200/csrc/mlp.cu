@@ -792,6 +792,7 @@ static int mlp_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaS
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (mlp_tc_supported(Pa) && (!Pb || mlp_tc_supported(Pb))) return mlp_tc_launch(Pa, Pb, B, st);
   if (mlp_all_packed(Pa) && (!Pb || mlp_all_packed(Pb))) {
     const int ldp = Pb ? (Pa->ld > Pb->ld ? Pa->ld : Pb->ld) : Pa->ld;
     bool done = false;

@@ -41,4 +41,8 @@ struct MlpParams2 {
   MlpParams a, b;
 };
 
+// tensor-core engine (mlp_tc.cu): runs when every layer of the launch carries the tc-packed weights (pcv_linear.Wt)
+bool mlp_tc_supported(const MlpParams *P);
+int mlp_tc_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaStream_t st);
+
 }  // namespace pcv

@@ -1,0 +1,442 @@
+// mlp_tc.cu — fused MLP blocks on the 5th-gen tensor cores (sm_100a), inference engine "tc".
+//
+// Replaces the same reference code as mlp.cu (pivotcvae.py:159-174, 204-240, 278-291; listcvae.py:106-119;
+// cvae.py:79-92; env/response_model.py:76-87): gather / one-hot / concat prologue -> Linear+activation chain ->
+// optional reparameterisation, one launch per block (or per chain of two blocks).
+//
+// The FFMA engines of mlp.cu are bit-identical to the CPU oracle but run at ~10 % of the fp32 peak (latency-bound:
+// 8-32 rows per CTA, a cluster barrier per layer).  Here a CTA owns 128 batch rows (= the 128 TMEM lanes) and the
+// whole layer chain stays on chip, TMEM-chained:
+//
+//   layer l accumulates  Y_l[128 x N_l] = X_l[128 x K_l] . W_l^T  in tensor memory (tcgen05.mma kind::tf32, M = 128,
+//   N = N_l <= 256, fp32 accumulators; two 256-column regions ping-pong between consecutive layers);
+//   8 transform warps (thread = batch row) read Y_l 32 columns at a time (tcgen05.ld), add the bias, apply the
+//   activation, split the fp32 result into tf32 hi + lo and write it as a [128 x 32] K-major SWIZZLE_128B chunk into a
+//   double-buffered shared-memory operand buffer: that chunk is 32 k-columns of X_{l+1}, and layer l+1's MMAs on it
+//   start at once while the next chunk is being transformed.  The activations never exist as a whole outside TMEM
+//   (a 128 x 256 fp32 tile split in hi/lo would be 256 KB: it does not fit shared memory), nothing goes to HBM
+//   between layers;
+//   a TMA warp streams the weights, pre-split and pre-swizzled by pcv_mlp_tc_pack into the [N][32] hi | lo images of
+//   each 32-k chunk (one bulk copy per chunk, 2 x 64 KB ring).
+//
+// Precision: "3xTF32" — every k-step issues hi*hi + lo*hi + hi*lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): the
+// products are good to ~2^-21 relative, the accumulation is fp32.  Not bit-identical to the oracle's sequential FMA
+// chain (a different, equally valid fp32 summation order): outputs agree with torch's addmm to ~1e-6 relative, the
+// same distance the FFMA chain is from it; the tests hold this engine to the reference fixtures (logits 1e-4, slates).
+#include "mlp_common.cuh"
+#include "tc_common.cuh"
+
+namespace pcv {
+
+constexpr int MT_BM = 128;                  // batch rows per CTA (TMEM lanes)
+constexpr int MT_KC = 32;                   // k-chunk: 32 fp32 = one 128-byte swizzle row
+constexpr int MT_MAXN = 256;                // widest layer (one TMEM region)
+constexpr int MT_MAXK0 = 64;                // widest assembled input (two operand chunks)
+constexpr int MT_STAGES = 2;                // weight ring
+constexpr uint32_t MT_STAGE_BYTES = MT_MAXN * 128 * 2;   // [hi | lo] images of a [256][32] weight chunk
+constexpr uint32_t MT_AHALF_BYTES = MT_BM * 128;         // one [128][32] image
+constexpr uint32_t MT_ABUF_BYTES = 2 * MT_AHALF_BYTES;   // [hi | lo]
+constexpr int MT_NABUF = 2;
+constexpr int MT_XWARPS = 8;                // transform warps: two groups of four (one warp per TMEM lane quarter)
+constexpr int MT_THREADS = 64 + 32 * MT_XWARPS;
+constexpr size_t MT_SMEM = (size_t)MT_STAGES * MT_STAGE_BYTES + (size_t)MT_NABUF * MT_ABUF_BYTES + 1024;
+
+__host__ __device__ __forceinline__ int mt_pad16(int n) { return (n + 15) & ~15; }
+__host__ __device__ __forceinline__ int mt_chunks(int kpad) { return (kpad + MT_KC - 1) / MT_KC; }
+__host__ __device__ __forceinline__ int64_t mt_packed_floats(int n_in, int n_out) {
+  return (int64_t)mt_chunks(mt_pad16(n_in)) * mt_pad16(n_out) * 64;
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// Weight images: chunk c (k = 32c .. 32c+31) = [hi: Npad x 128 B][lo: Npad x 128 B], row n = 32 floats whose
+// 16-byte units are XOR-swizzled with (n & 7) (the K-major SWIZZLE_128B layout); rows >= n_out and k >= n_in are zero.
+__global__ void mlp_tc_pack_kernel(const float *__restrict__ W, int K, int NO, float *__restrict__ out, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int npad = mt_pad16(NO);
+  const int64_t per_chunk = (int64_t)npad * 64;
+  const int c = (int)(e / per_chunk);
+  const int rem = (int)(e - (int64_t)c * per_chunk);
+  const int half = rem / (npad * 32);
+  const int p = rem - half * npad * 32;
+  const int n = p >> 5, pos = p & 31;
+  const int unit = (pos >> 2) ^ (n & 7);
+  const int k = c * MT_KC + unit * 4 + (pos & 3);
+  const float v = (n < NO && k < K) ? W[(int64_t)n * K + k] : 0.f;
+  const float hi = __uint_as_float(tf32_rna(v));
+  out[e] = half ? __uint_as_float(tf32_rna(v - hi)) : hi;
+}
+
+struct MtBars {
+  unsigned long long wfull[MT_STAGES], wempty[MT_STAGES], afull[MT_NABUF], aempty[MT_NABUF], accfull;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t mt_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// one 16-byte unit (4 consecutive k of one row): fp32 -> tf32 hi | lo images
+__device__ __forceinline__ void mt_store_unit(uint32_t addr_hi, float x0, float x1, float x2, float x3) {
+  const uint32_t h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+  st_shared_v4(addr_hi, h0, h1, h2, h3);
+  st_shared_v4(addr_hi + MT_AHALF_BYTES, tf32_rna(x0 - __uint_as_float(h0)), tf32_rna(x1 - __uint_as_float(h1)),
+               tf32_rna(x2 - __uint_as_float(h2)), tf32_rna(x3 - __uint_as_float(h3)));
+}
+
+__global__ void __launch_bounds__(MT_THREADS, 1)
+mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
+  extern __shared__ unsigned char mt_smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(mt_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage0 = smem_u32(smem);
+  const uint32_t abuf0 = stage0 + MT_STAGES * MT_STAGE_BYTES;
+  __shared__ MtBars Bq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b0 = (int64_t)blockIdx.x * MT_BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MT_STAGES; ++s) { mbar_init(&Bq.wfull[s], 1); mbar_init(&Bq.wempty[s], 1); }
+    for (int a = 0; a < MT_NABUF; ++a) { mbar_init(&Bq.afull[a], MT_BM); mbar_init(&Bq.aempty[a], 1); }
+    mbar_init(&Bq.accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&Bq.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = Bq.tmem_base;
+
+  if (warp == 0) {
+    // ---------------- weight producer ----------------
+    // cold start (e.g. after other work evicted them): request the weight images of the whole launch into L2, the
+    // CTAs taking turns over the 128-byte lines
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const pcv_mlp_desc &d = blk ? P2.b.d : P2.a.d;
+      for (int l = 0; l < d.n_layers; ++l) {
+        const char *src = reinterpret_cast<const char *>(d.layer[l].Wt);
+        const int64_t lines = mt_packed_floats(d.layer[l].n_in, d.layer[l].n_out) / 32;
+        for (int64_t i = (int64_t)blockIdx.x * 32 + lane; i < lines; i += (int64_t)gridDim.x * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + i * 128));
+      }
+    }
+    if (lane == 0) {
+      uint32_t gw = 0;
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const pcv_mlp_desc &d = blk ? P2.b.d : P2.a.d;
+        for (int l = 0; l < d.n_layers; ++l) {
+          const int npad = mt_pad16(d.layer[l].n_out);
+          const int nch = mt_chunks(mt_pad16(d.layer[l].n_in));
+          const uint32_t bytes = (uint32_t)npad * 256u;
+          const float *src = d.layer[l].Wt;
+          for (int c = 0; c < nch; ++c, ++gw) {
+            const uint32_t s = gw % MT_STAGES;
+            mbar_wait(&Bq.wempty[s], ((gw / MT_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&Bq.wfull[s], bytes);
+            tma_bulk_load(smem + (size_t)s * MT_STAGE_BYTES, src + (int64_t)c * npad * 64, bytes, &Bq.wfull[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (the whole warp, converged; one elected lane issues: tc_common.cuh) ----------------
+    uint32_t ga = 0, gw = 0, gl = 0;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const pcv_mlp_desc &d = blk ? P2.b.d : P2.a.d;
+      for (int l = 0; l < d.n_layers; ++l, ++gl) {
+        const int kpad = mt_pad16(d.layer[l].n_in), npad = mt_pad16(d.layer[l].n_out);
+        const int nch = mt_chunks(kpad);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(MT_BM >> 4) << 24);
+        const uint32_t tacc = tmem + (gl & 1) * MT_MAXN;
+        for (int c = 0; c < nch; ++c, ++ga, ++gw) {
+          const uint32_t ab = ga & 1, s = gw % MT_STAGES;
+          mbar_wait(&Bq.afull[ab], (ga >> 1) & 1);
+          mbar_wait(&Bq.wfull[s], (gw / MT_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = abuf0 + ab * MT_ABUF_BYTES, a_lo = a_hi + MT_AHALF_BYTES;
+          const uint32_t w_hi = stage0 + s * MT_STAGE_BYTES, w_lo = w_hi + (uint32_t)npad * 128u;
+          const int atoms = min(4, (kpad - c * MT_KC) >> 3);
+          for (int j = 0; j < atoms; ++j) {   // one k-step = 8 fp32 = 32 B inside the 128-byte swizzle row
+            const uint64_t dah = mt_desc_sw128(a_hi + j * 32), dal = mt_desc_sw128(a_lo + j * 32);
+            const uint64_t dbh = mt_desc_sw128(w_hi + j * 32), dbl = mt_desc_sw128(w_lo + j * 32);
+            umma_tf32_elect(tacc, dal, dbh, idesc, (c | j) != 0);   // small terms first, the leading product last
+            umma_tf32_elect(tacc, dah, dbl, idesc, 1);
+            umma_tf32_elect(tacc, dah, dbh, idesc, 1);
+          }
+          umma_commit_elect(&Bq.wempty[s]);
+          umma_commit_elect(&Bq.aempty[ab]);
+        }
+        umma_commit_elect(&Bq.accfull);
+      }
+    }
+  } else {
+    // ---------------- transform warps: thread = batch row = TMEM lane ----------------
+    const int grp = (warp - 2) >> 2;             // group g produces the operand chunks with (sequence number & 1) == g
+    const int quarter = warp & 3;                // TMEM lane quarter = warp id % 4
+    const int r = quarter * 32 + lane;
+    const int64_t b = b0 + r;
+    const uint32_t rowoff = (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint32_t ga = 0, gl = 0;
+    auto acquire = [&](uint32_t g) {   // operand buffer of production g is free: the MMAs of production g - 2 have read it
+      mbar_wait(&Bq.aempty[g & 1], ((g >> 1) & 1) ^ 1);
+    };
+    auto publish = [&](uint32_t g) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&Bq.afull[g & 1]);
+    };
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const MlpParams &P = blk ? P2.b : P2.a;
+      const pcv_mlp_desc &d = P.d;
+      const int k0pad = mt_pad16(P.n_in0);
+      const int nch0 = mt_chunks(k0pad);
+      if (grp == 0) {
+        // ---- prologue: assemble x0 = [segments] (this thread: its own row), normalise, split, publish
+        if (blk > 0) {
+          // block b reads what block a's epilogue wrote for the same batch rows (z), possibly by another thread
+          __threadfence_block();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        for (int c = 0; c < nch0; ++c) acquire(ga + c);
+        auto eaddr = [&](int e) {   // raw fp32 staging = the hi image of the chunk
+          const uint32_t kk = (uint32_t)e & 31u;
+          return abuf0 + ((ga + ((uint32_t)e >> 5)) & 1u) * MT_ABUF_BYTES + rowoff + ((((kk >> 2) ^ sw)) << 4) + ((kk & 3u) << 2);
+        };
+        for (int e = 0; e < nch0 * MT_KC; ++e) st_shared_f32(eaddr(e), 0.f);
+        if (b < B) {
+          for (int s = 0; s < d.n_segments; ++s) {
+            const pcv_segment &sg = d.seg[s];
+            const int off = P.seg_off[s];
+            if (sg.kind == PCV_SEG_DENSE) {
+              const float *src = (const float *)sg.ptr + b * sg.width;
+              for (int e = 0; e < sg.width; ++e) st_shared_f32(eaddr(off + e), __ldg(src + e));
+            } else if (sg.kind == PCV_SEG_ONEHOT) {
+              const float *rr = (const float *)sg.ptr + b * sg.count;
+              float sum = 0.f;
+              for (int l = 0; l < sg.count; ++l) sum += rr[l];
+              const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
+              if (hot >= 0 && hot <= sg.count) st_shared_f32(eaddr(off + hot), 1.f);
+            } else {  // GATHER
+              const float *tab = (const float *)sg.ptr;
+              const bool vec = (sg.width & 3) == 0 && ((reinterpret_cast<uintptr_t>(tab) & 15) == 0);
+              for (int c = 0; c < sg.count; ++c) {
+                const float *row = tab + sg.idx[b * sg.count + c] * (int64_t)sg.width;
+                const int e0 = off + c * sg.width;
+                if (vec) {
+                  for (int k = 0; k < sg.width; k += 4) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4 *>(row + k));
+                    st_shared_f32(eaddr(e0 + k), t4.x); st_shared_f32(eaddr(e0 + k + 1), t4.y);
+                    st_shared_f32(eaddr(e0 + k + 2), t4.z); st_shared_f32(eaddr(e0 + k + 3), t4.w);
+                  }
+                } else {
+                  for (int k = 0; k < sg.width; ++k) st_shared_f32(eaddr(e0 + k), __ldg(row + k));
+                }
+              }
+            }
+          }
+          // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order as in mlp.cu
+          for (int s = 0; s < d.n_segments; ++s) {
+            if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
+            const int off = P.seg_off[s], w = P.seg_off[s + 1] - off;
+            float ss = 0.f;
+            for (int e = 0; e < w; ++e) { const float v = ld_shared_f32(eaddr(off + e)); ss = fmaf(v, v, ss); }
+            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+            for (int e = 0; e < w; ++e) st_shared_f32(eaddr(off + e), ld_shared_f32(eaddr(off + e)) / nrm);
+          }
+          if (d.copy_seg >= 0) {
+            const int off = P.seg_off[d.copy_seg], w = P.seg_off[d.copy_seg + 1] - off;
+            float *dst = d.out + b * d.out_ld;
+            for (int e = 0; e < w; ++e) dst[e] = ld_shared_f32(eaddr(off + e));
+          }
+        }
+        for (int c = 0; c < nch0; ++c) {
+          const uint32_t base = abuf0 + ((ga + c) & 1u) * MT_ABUF_BYTES + rowoff;
+#pragma unroll
+          for (uint32_t u = 0; u < 8; ++u) {
+            const float4 x = ld_shared_v4(base + (u << 4));
+            mt_store_unit(base + (u << 4), x.x, x.y, x.z, x.w);
+          }
+        }
+        for (int c = 0; c < nch0; ++c) publish(ga + c);
+      }
+      ga += nch0;
+
+      for (int l = 0; l < d.n_layers; ++l, ++gl) {
+        const pcv_linear &L = d.layer[l];
+        const bool last = (l == d.n_layers - 1);
+        mbar_wait(&Bq.accfull, gl & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = lane_base + (gl & 1) * MT_MAXN;
+        if (!last) {
+          const int nchn = mt_chunks(mt_pad16(L.n_out));
+          for (int c = 0; c < nchn; ++c) {
+            const uint32_t g = ga + c;
+            if ((int)(g & 1) != grp) continue;
+            acquire(g);
+            uint32_t v[32];
+            TC_LD32(v, tacc + (uint32_t)(c * MT_KC));
+            const int nb = c * MT_KC;
+            float bias[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bias[i] = (nb + i < L.n_out) ? __ldg(L.b + nb + i) : 0.f;
+            TC_WAIT_LD(v);
+            const uint32_t base = abuf0 + (g & 1u) * MT_ABUF_BYTES + rowoff;
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u) {
+              float x[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) x[i] = apply_act(__uint_as_float(v[4 * u + i]) + bias[4 * u + i], L.act);
+              mt_store_unit(base + ((u ^ sw) << 4), x[0], x[1], x[2], x[3]);
+            }
+            publish(g);
+          }
+          ga += nchn;
+        } else if (grp == 0) {
+          // ---- final epilogue: bias + activation -> out (+ reparameterisation)
+          const bool vec = b < B && ((d.out_ld | d.out_col0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+          float *orow = d.out + (b < B ? b : 0) * d.out_ld + d.out_col0;
+          for (int nb = 0; nb < L.n_out; nb += 32) {
+            uint32_t v[32];
+            TC_LD32(v, tacc + (uint32_t)nb);
+            float bias[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bias[i] = (nb + i < L.n_out) ? __ldg(L.b + nb + i) : 0.f;
+            TC_WAIT_LD(v);
+            if (b < B) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = apply_act(__uint_as_float(v[i + j]) + bias[i + j], L.act);
+                if (vec && nb + i + 4 <= L.n_out) {
+                  *reinterpret_cast<float4 *>(orow + nb + i) = make_float4(x[0], x[1], x[2], x[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (nb + i + j < L.n_out) orow[nb + i + j] = x[j];
+                }
+              }
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (d.latent > 0 && b < B) {
+            // cvae.py:79-83: z = eps * exp(0.5 * logvar) + mu; this thread re-reads the [mu | logvar] row it just wrote
+            const int Z = d.latent;
+            const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
+            for (int j = 0; j < Z; ++j) {
+              const float mu = orow[j], lv = orow[Z + j];
+              float eps;
+              if (d.eps) {
+                eps = d.eps[b * Z + j];
+              } else {
+                float n4[4];
+                normal4(d.seed, rng_off, b, j >> 2, n4);
+                eps = n4[j & 3];
+              }
+              const float sd = pcv_expf(lv * 0.5f);
+              d.z[b * Z + j] = eps * sd + mu;
+              if (d.eps_out) d.eps_out[b * Z + j] = eps;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
+}
+
+bool mlp_tc_supported(const MlpParams *P) {
+  const pcv_mlp_desc &d = P->d;
+  if (P->n_in0 > MT_MAXK0 || d.x0 != nullptr) return false;
+  for (int l = 0; l < d.n_layers; ++l) {
+    if (d.layer[l].Wt == nullptr || d.layer[l].n_out > MT_MAXN) return false;
+    if (l < d.n_layers - 1 && d.acts[l] != nullptr) return false;
+  }
+  return true;
+}
+
+int mlp_tc_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaStream_t st) {
+  MlpParams2 P2;
+  P2.a = *Pa;
+  P2.b = Pb ? *Pb : *Pa;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_set[64] = {false};
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM);
+    if (e != cudaSuccess) {
+      set_error("pcv_mlp_fwd (tc engine): cudaFuncSetAttribute -> %s", cudaGetErrorString(e));
+      return PCV_ERR_CUDA;
+    }
+    attr_set[dev & 63] = true;
+  }
+  const int64_t blocks = (B + MT_BM - 1) / MT_BM;
+  mlp_tc_kernel<<<(unsigned)blocks, MT_THREADS, MT_SMEM, st>>>(P2, Pb ? 2 : 1, B);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("pcv_mlp_fwd (tc engine): kernel launch -> %s", cudaGetErrorString(e));
+    return PCV_ERR_CUDA;
+  }
+  count_launch();
+  return PCV_OK;
+}
+
+}  // namespace pcv
+
+using namespace pcv;
+
+extern "C" {
+
+size_t pcv_mlp_tc_packed_bytes(int n_in, int n_out) {
+  if (n_in <= 0 || n_out <= 0) return 0;
+  return (size_t)mt_packed_floats(n_in, n_out) * sizeof(float);
+}
+
+int pcv_mlp_tc_pack(const float *W, int n_in, int n_out, float *packed, pcv_stream_t stream) {
+  PCV_CHECK_ARG(W && packed, "NULL pointer");
+  PCV_CHECK_ARG(n_in > 0 && n_out > 0 && n_in <= PCV_MAX_WIDTH && n_out <= PCV_MAX_WIDTH, "bad layer shape");
+  PCV_CHECK_ARG(((uintptr_t)packed & 127) == 0, "packed buffer must be 128-byte aligned");
+  int rc = check_arch();
+  if (rc != PCV_OK) return rc;
+  const int64_t total = mt_packed_floats(n_in, n_out);
+  mlp_tc_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, n_in, n_out, packed, total);
+  PCV_LAUNCH_CHECK();
+  return PCV_OK;
+}
+
+}  // extern "C"

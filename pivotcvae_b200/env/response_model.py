@@ -12,6 +12,7 @@ from torch import nn
 
 from .. import _lib as L
 from .. import ops
+from ..models.cvae import with_mlp_engine
 
 
 def sample_users(environment, batch_size):
@@ -56,6 +57,9 @@ class UserResponseModel_MLP(Environment):
             self.mlp.append(m)
             self.add_module("mlp_%d" % (i + 1), m)
 
+    mlp_engine = None   # None = ops.MLP_ENGINE; "tc" = the tcgen05 engine of the fused block (models/cvae.py)
+
+    @with_mlp_engine
     def forward(self, slates, users):
         """gather L rows -> L2-normalise the flattened slate vector -> [+ normalised user row]
         -> Linear/ReLU chain -> (B, L) logits (response_model.py:76-87); one fused kernel."""

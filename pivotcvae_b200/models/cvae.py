@@ -13,6 +13,20 @@ from ..autograd import FusedMLPFn, MlpSpec
 from ..noise import NoiseSource
 
 
+def with_mlp_engine(fn):
+    """Run a method under the object's `mlp_engine` ("exact" / "tc"; None = the process default ops.MLP_ENGINE)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        eng = getattr(self, "mlp_engine", None)
+        if eng is None:
+            return fn(self, *a, **k)
+        with ops.mlp_engine(eng):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 def _require_cuda(device):
     dev = torch.device(device)
     if dev.type != "cuda":
@@ -21,6 +35,10 @@ def _require_cuda(device):
 
 
 class BaseCVAE(nn.Module):
+    # inference engine of the fused MLP blocks in recommend(): None = ops.MLP_ENGINE (default "exact": the FFMA engines,
+    # bit-identical to the CPU oracle); "tc" = tcgen05 3xTF32 (csrc/mlp_tc.cu), fp32-grade, several times faster
+    mlp_engine = None
+
     def __init__(self, embeddings, u_embeddings, slate_size, latent_size, no_user, device, fine_tune=False):
         super().__init__()
         self.candidateFlag = False

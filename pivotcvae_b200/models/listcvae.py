@@ -5,7 +5,7 @@ Same as PivotCVAE minus the pivot: one decoder MLP emits all L*D slate features.
 import torch
 
 from .. import _lib as L
-from .cvae import BaseCVAE
+from .cvae import BaseCVAE, with_mlp_engine
 
 
 class UserListCVAEWithPrior(BaseCVAE):
@@ -55,6 +55,7 @@ class UserListCVAEWithPrior(BaseCVAE):
         p = self._logits(rx.view(-1, self.feature_size), candidates)
         return p, rx, z, emb, mu, lv
 
+    @with_mlp_engine
     def recommend(self, r, u=None, return_item=False):
         """listcvae.py:170-188."""
         with torch.no_grad():

@@ -11,7 +11,7 @@ strings; the reference's class names are kept so pickles and imports resolve.
 import torch
 
 from .. import _lib as L
-from .cvae import BaseCVAE
+from .cvae import BaseCVAE, with_mlp_engine
 
 
 class UserPivotCVAE(BaseCVAE):
@@ -125,6 +125,7 @@ class UserPivotCVAE(BaseCVAE):
         p = self._logits(rx.view(-1, self.feature_size), candidates)
         return p, rx.view(B, self.slate_size, self.feature_size), z, emb, mu, lv
 
+    @with_mlp_engine
     def recommend(self, r, u=None, return_item=False, random_pivot=False):
         """prior -> z -> pivot -> slate completion -> arg-max items (pivotcvae.py:278-296)."""
         with torch.no_grad():

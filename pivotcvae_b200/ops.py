@@ -340,7 +340,7 @@ class Gather:
 # IN PLACE when the tensor's version counter moves (so CUDA graphs that captured the pointer stay valid
 # after `repack_stale()`).  An entry pins the weight's storage, so a data_ptr can not be recycled by
 # another tensor while it is cached.
-_PACKED = collections.OrderedDict()   # data_ptr -> [version, shape, storage, packed, weight]
+_PACKED = collections.OrderedDict()   # (data_ptr, kind) -> [version, shape, storage, packed, weight, kind]
 _PACKED_MAX = 512
 _PACKED_PINNED = set()                # keys a live CUDA graph reads through: never evicted
 
@@ -351,26 +351,31 @@ def pin_packed():
     _PACKED_PINNED.update(_PACKED.keys())
 
 
-def _pack_into(W, packed):
+def _pack_into(W, packed, kind):
     with torch.cuda.device(W.device):
-        L.check(L.load().pcv_mlp_pack(_ptr(W), W.shape[1], W.shape[0], _ptr(packed), _stream()), "pcv_mlp_pack")
+        if kind == "tc":
+            L.check(L.load().pcv_mlp_tc_pack(_ptr(W), W.shape[1], W.shape[0], _ptr(packed), _stream()), "pcv_mlp_tc_pack")
+        else:
+            L.check(L.load().pcv_mlp_pack(_ptr(W), W.shape[1], W.shape[0], _ptr(packed), _stream()), "pcv_mlp_pack")
 
 
-def packed_weight(W):
-    """Pre-tiled copy of an nn.Linear weight for pcv_linear.Wp (cached per tensor + version)."""
-    key = W.data_ptr()
+def packed_weight(W, kind="ffma"):
+    """Pre-tiled copy of an nn.Linear weight (cached per tensor + version): kind "ffma" = pcv_linear.Wp (the
+    packed-weight cluster engine), kind "tc" = pcv_linear.Wt (tf32 hi | lo images of the tensor-core engine)."""
+    key = (W.data_ptr(), kind)
     hit = _PACKED.get(key)
     if hit is not None and hit[1] == tuple(W.shape):
         if hit[0] != W._version:
-            _pack_into(W, hit[3])
+            _pack_into(W, hit[3], kind)
             hit[0] = W._version
         _PACKED.move_to_end(key)
         return hit[3]
-    nbytes = L.load().pcv_mlp_packed_bytes(W.shape[1], W.shape[0])
+    lib = L.load()
+    nbytes = (lib.pcv_mlp_tc_packed_bytes if kind == "tc" else lib.pcv_mlp_packed_bytes)(W.shape[1], W.shape[0])
     packed = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
-    _pack_into(W, packed)
+    _pack_into(W, packed, kind)
     if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not outlive its graph in the cache
-        _PACKED[key] = [W._version, tuple(W.shape), W.untyped_storage(), packed, W]
+        _PACKED[key] = [W._version, tuple(W.shape), W.untyped_storage(), packed, W, kind]
         while len(_PACKED) > _PACKED_MAX:
             victim = next((k for k in _PACKED if k not in _PACKED_PINNED), None)
             if victim is None:
@@ -384,15 +389,37 @@ def repack_stale():
     updating weights that a captured CUDA graph reads through the packed copies."""
     for hit in _PACKED.values():
         if hit[0] != hit[4]._version:
-            _pack_into(hit[4], hit[3])
+            _pack_into(hit[4], hit[3], hit[5])
             hit[0] = hit[4]._version
 
 
 PACK_WEIGHTS = True   # False: always stream nn.Linear weights as they are (the training engine)
+# Inference engine of the fused MLP blocks: "exact" = the FFMA engines (sequential-k FMA chain, bit-identical to the
+# CPU oracle); "tc" = the tcgen05 3xTF32 engine (csrc/mlp_tc.cu: fp32-grade, ~1e-6 of torch's addmm, several times
+# faster) wherever a block fits it (input <= 64 wide, layers <= 256 wide), the exact engines elsewhere.
+MLP_ENGINE = "exact"
+TC_MAX_IN, TC_MAX_WIDTH = 64, 256
+
+
+class mlp_engine:
+    """Context manager: `with ops.mlp_engine("tc"): ...`"""
+
+    def __init__(self, name):
+        if name not in ("exact", "tc"):
+            raise ValueError("mlp engine must be 'exact' or 'tc'")
+        self.name = name
+
+    def __enter__(self):
+        global MLP_ENGINE
+        self.prev, MLP_ENGINE = MLP_ENGINE, self.name
+
+    def __exit__(self, *exc):
+        global MLP_ENGINE
+        MLP_ENGINE = self.prev
 
 
 def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_seg=-1, save=False,
-              latent=0, eps=None, seed=0, offset=0, offset_dev=None):
+              latent=0, eps=None, seed=0, offset=0, offset_dev=None, engine=None):
     """Build a pcv_mlp_desc (+ its output tensors); returns (desc, results, keep-alive list, device)."""
     if len(segments) > L.PCV_MAX_SEGMENTS or len(layers) > L.PCV_MAX_LAYERS:
         raise L.PcvError("too many segments / layers for one fused block")
@@ -402,6 +429,11 @@ def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_se
     for i, s in enumerate(segments):
         s.fill(d.seg[i], keep)
     n_in0 = sum(s.width for s in segments)
+    engine = engine or MLP_ENGINE
+    if engine not in ("exact", "tc"):
+        raise ValueError("mlp engine must be 'exact' or 'tc'")
+    tc = (engine == "tc" and not save and PACK_WEIGHTS and n_in0 <= TC_MAX_IN
+          and all(W.shape[0] <= TC_MAX_WIDTH for W, _, _ in layers))
     d.n_layers = len(layers)
     prev = n_in0
     dev = None
@@ -412,8 +444,11 @@ def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_se
         d.layer[i].n_in, d.layer[i].n_out, d.layer[i].act = W.shape[1], W.shape[0], act
         keep.extend([W, b])
         if not save and PACK_WEIGHTS:
-            Wp = packed_weight(W)
-            d.layer[i].Wp = Wp.data_ptr()
+            Wp = packed_weight(W, "tc" if tc else "ffma")
+            if tc:
+                d.layer[i].Wt = Wp.data_ptr()
+            else:
+                d.layer[i].Wp = Wp.data_ptr()
             keep.append(Wp)
         prev = W.shape[0]
     n_out = prev
