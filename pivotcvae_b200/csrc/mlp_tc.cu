@@ -10,19 +10,25 @@
 //
 //   layer l accumulates  Y_l[128 x N_l] = X_l[128 x K_l] . W_l^T  in tensor memory (tcgen05.mma kind::tf32, M = 128,
 //   N = N_l <= 256, fp32 accumulators; two 256-column regions ping-pong between consecutive layers);
-//   8 transform warps (thread = batch row) read Y_l 32 columns at a time (tcgen05.ld), add the bias, apply the
-//   activation, split the fp32 result into tf32 hi + lo and write it as a [128 x 32] K-major SWIZZLE_128B chunk into a
-//   double-buffered shared-memory operand buffer: that chunk is 32 k-columns of X_{l+1}, and layer l+1's MMAs on it
-//   start at once while the next chunk is being transformed.  The activations never exist as a whole outside TMEM
-//   (a 128 x 256 fp32 tile split in hi/lo would be 256 KB: it does not fit shared memory), nothing goes to HBM
-//   between layers;
+//   8 transform warps (thread = batch row, two groups of four) read Y_l 32 columns at a time (tcgen05.ld), add the
+//   bias, apply the activation, split the fp32 result into tf32 hi + lo and write it as a [128 x 32] K-major
+//   SWIZZLE_128B chunk into a double-buffered shared-memory operand buffer: that chunk is 32 k-columns of X_{l+1},
+//   and layer l+1's MMAs on it start at once while the next chunk is being transformed.  The activations never exist
+//   as a whole outside TMEM (a 128 x 256 fp32 tile split in hi/lo would be 256 KB: it does not fit shared memory),
+//   nothing goes to HBM between layers;
 //   a TMA warp streams the weights, pre-split and pre-swizzled by pcv_mlp_tc_pack into the [N][32] hi | lo images of
 //   each 32-k chunk (one bulk copy per chunk, 2 x 64 KB ring).
+// (Splitting a row tile's columns over a cluster of CTAs was built and measured first: the all-gather of the operand
+// chunks through distributed shared memory moves 3 x 32 KB per chunk at ~20 B/clk/SM — slower than the MMAs it saves.)
 //
-// Precision: "3xTF32" — every k-step issues hi*hi + lo*hi + hi*lo with hi = rna_tf32(x), lo = rna_tf32(x - hi): the
-// products are good to ~2^-21 relative, the accumulation is fp32.  Not bit-identical to the oracle's sequential FMA
-// chain (a different, equally valid fp32 summation order): outputs agree with torch's addmm to ~1e-6 relative, the
-// same distance the FFMA chain is from it; the tests hold this engine to the reference fixtures (logits 1e-4, slates).
+// Precision: "3xTF32" — lo*hi + hi*lo + hi*hi with hi = rna_tf32(x), lo = rna_tf32(x - hi): products good to ~2^-21.
+// The tensor core TRUNCATES its fp32 accumulator on every MMA (measured, profiles/probe_tc_accum.py: a bias of about
+// -0.75 x 2^-24 of the accumulator per accumulating MMA; the 96 interleaved MMAs of a 256-deep layer cost -4e-6, 15x
+// the error of an fp32 FMA chain).  Layers deeper than 64 therefore run in TWO PASSES over their operand chunks: first
+// every small term (lo*hi, hi*lo — while the accumulator is ~2^-11 of its final size their truncations are
+// negligible), then the 32 hi*hi MMAs; the transform warps simply produce the chunks twice (the second time hi only).
+// Result: fp32-grade (a few times the distance an fp32 FMA chain has from exact), NOT bit-identical to the oracle's
+// sequential chain; the tests hold this engine to the reference fixtures (logits 1e-4, identical slates).
 #include "mlp_common.cuh"
 #include "tc_common.cuh"
 
@@ -31,7 +37,8 @@ namespace pcv {
 constexpr int MT_BM = 128;                  // batch rows per CTA (TMEM lanes)
 constexpr int MT_KC = 32;                   // k-chunk: 32 fp32 = one 128-byte swizzle row
 constexpr int MT_MAXN = 256;                // widest layer (one TMEM region)
-constexpr int MT_MAXK0 = 64;                // widest assembled input (two operand chunks)
+constexpr int MT_MAXK0 = 64;                // widest assembled input (two operand chunks = both operand buffers)
+constexpr int MT_TWOPASS_K = 64;            // layers deeper than this: small terms first, then hi*hi (see above)
 constexpr int MT_STAGES = 2;                // weight ring
 constexpr uint32_t MT_STAGE_BYTES = MT_MAXN * 128 * 2;   // [hi | lo] images of a [256][32] weight chunk
 constexpr uint32_t MT_AHALF_BYTES = MT_BM * 128;         // one [128][32] image
@@ -72,6 +79,14 @@ __global__ void mlp_tc_pack_kernel(const float *__restrict__ W, int K, int NO, f
   out[e] = half ? __uint_as_float(tf32_rna(v - hi)) : hi;
 }
 
+#ifdef PCV_TC_TRACE
+// CTA 0: role 0 = first transform warp, role 1 = MMA warp; clock64 stamps (profiles/trace_mlp_tc.py)
+__device__ long long g_mt_trace[2][64];
+#define MT_TRACE(role, i) do { if (blockIdx.x == 0 && lane == 0 && warp == ((role) == 0 ? 2 : 1) && (i) < 64) g_mt_trace[role][i] = clock64(); } while (0)
+#else
+#define MT_TRACE(role, i) do { } while (0)
+#endif
+
 struct MtBars {
   unsigned long long wfull[MT_STAGES], wempty[MT_STAGES], afull[MT_NABUF], aempty[MT_NABUF], accfull;
   uint32_t tmem_base;
@@ -102,14 +117,8 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
-
-// one 16-byte unit (4 consecutive k of one row): fp32 -> tf32 hi | lo images
-__device__ __forceinline__ void mt_store_unit(uint32_t addr_hi, float x0, float x1, float x2, float x3) {
-  const uint32_t h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
-  st_shared_v4(addr_hi, h0, h1, h2, h3);
-  st_shared_v4(addr_hi + MT_AHALF_BYTES, tf32_rna(x0 - __uint_as_float(h0)), tf32_rna(x1 - __uint_as_float(h1)),
-               tf32_rna(x2 - __uint_as_float(h2)), tf32_rna(x3 - __uint_as_float(h3)));
-}
+// branch-free activation: v > 0 ? v : slope * v (slope 1 / 0.01 / 0 = none / LeakyReLU / ReLU)
+__device__ __forceinline__ float mt_act(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
 mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
@@ -120,10 +129,12 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
   __shared__ MtBars Bq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b0 = (int64_t)blockIdx.x * MT_BM;
+  MT_TRACE(1, 61);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MT_STAGES; ++s) { mbar_init(&Bq.wfull[s], 1); mbar_init(&Bq.wempty[s], 1); }
-    for (int a = 0; a < MT_NABUF; ++a) { mbar_init(&Bq.afull[a], MT_BM); mbar_init(&Bq.aempty[a], 1); }
+    // afull: one elected arrive per producing warp (every operand chunk is written by four warps)
+    for (int a = 0; a < MT_NABUF; ++a) { mbar_init(&Bq.afull[a], 4); mbar_init(&Bq.aempty[a], 1); }
     mbar_init(&Bq.accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,6 +146,7 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = Bq.tmem_base;
+  MT_TRACE(1, 62);
 
   if (warp == 0) {
     // ---------------- weight producer ----------------
@@ -154,15 +166,18 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
       for (int blk = 0; blk < n_blocks; ++blk) {
         const pcv_mlp_desc &d = blk ? P2.b.d : P2.a.d;
         for (int l = 0; l < d.n_layers; ++l) {
-          const int npad = mt_pad16(d.layer[l].n_out);
-          const int nch = mt_chunks(mt_pad16(d.layer[l].n_in));
-          const uint32_t bytes = (uint32_t)npad * 256u;
+          const int npad = mt_pad16(d.layer[l].n_out), kpad = mt_pad16(d.layer[l].n_in);
+          const int nch = mt_chunks(kpad);
+          const int passes = kpad > MT_TWOPASS_K ? 2 : 1;
           const float *src = d.layer[l].Wt;
-          for (int c = 0; c < nch; ++c, ++gw) {
-            const uint32_t s = gw % MT_STAGES;
-            mbar_wait(&Bq.wempty[s], ((gw / MT_STAGES) & 1) ^ 1);
-            mbar_expect_tx(&Bq.wfull[s], bytes);
-            tma_bulk_load(smem + (size_t)s * MT_STAGE_BYTES, src + (int64_t)c * npad * 64, bytes, &Bq.wfull[s]);
+          for (int p = 0; p < passes; ++p) {
+            const uint32_t bytes = (uint32_t)npad * (p == 0 ? 256u : 128u);   // second pass: the hi image only
+            for (int c = 0; c < nch; ++c, ++gw) {
+              const uint32_t s = gw % MT_STAGES;
+              mbar_wait(&Bq.wempty[s], ((gw / MT_STAGES) & 1) ^ 1);
+              mbar_expect_tx(&Bq.wfull[s], bytes);
+              tma_bulk_load(smem + (size_t)s * MT_STAGE_BYTES, src + (int64_t)c * npad * 64, bytes, &Bq.wfull[s]);
+            }
           }
         }
       }
@@ -175,32 +190,47 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
       for (int l = 0; l < d.n_layers; ++l, ++gl) {
         const int kpad = mt_pad16(d.layer[l].n_in), npad = mt_pad16(d.layer[l].n_out);
         const int nch = mt_chunks(kpad);
+        const int passes = kpad > MT_TWOPASS_K ? 2 : 1;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(MT_BM >> 4) << 24);
         const uint32_t tacc = tmem + (gl & 1) * MT_MAXN;
-        for (int c = 0; c < nch; ++c, ++ga, ++gw) {
-          const uint32_t ab = ga & 1, s = gw % MT_STAGES;
-          mbar_wait(&Bq.afull[ab], (ga >> 1) & 1);
-          mbar_wait(&Bq.wfull[s], (gw / MT_STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = abuf0 + ab * MT_ABUF_BYTES, a_lo = a_hi + MT_AHALF_BYTES;
-          const uint32_t w_hi = stage0 + s * MT_STAGE_BYTES, w_lo = w_hi + (uint32_t)npad * 128u;
-          const int atoms = min(4, (kpad - c * MT_KC) >> 3);
-          for (int j = 0; j < atoms; ++j) {   // one k-step = 8 fp32 = 32 B inside the 128-byte swizzle row
-            const uint64_t dah = mt_desc_sw128(a_hi + j * 32), dal = mt_desc_sw128(a_lo + j * 32);
-            const uint64_t dbh = mt_desc_sw128(w_hi + j * 32), dbl = mt_desc_sw128(w_lo + j * 32);
-            umma_tf32_elect(tacc, dal, dbh, idesc, (c | j) != 0);   // small terms first, the leading product last
-            umma_tf32_elect(tacc, dah, dbl, idesc, 1);
-            umma_tf32_elect(tacc, dah, dbh, idesc, 1);
+        uint32_t acc = 0;     // the layer's first MMA overwrites the accumulator
+        for (int p = 0; p < passes; ++p) {
+          for (int c = 0; c < nch; ++c, ++ga, ++gw) {
+            const uint32_t ab = ga & 1, s = gw % MT_STAGES;
+            mbar_wait(&Bq.afull[ab], (ga >> 1) & 1);
+            if (c == 0 && p == 0) MT_TRACE(1, blk * 26 + 4 + 6 * l);
+            mbar_wait(&Bq.wfull[s], (gw / MT_STAGES) & 1);
+            if (c == 0 && p == 0) MT_TRACE(1, blk * 26 + 5 + 6 * l);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = abuf0 + ab * MT_ABUF_BYTES, w_hi = stage0 + s * MT_STAGE_BYTES;
+            // descriptors of the chunk's first k-step; a k-step (8 fp32 = 32 B inside the 128-byte swizzle row) adds 2 to
+            // the encoded start address
+            uint64_t dah = mt_desc_sw128(a_hi), dal = mt_desc_sw128(a_hi + MT_AHALF_BYTES);
+            uint64_t dbh = mt_desc_sw128(w_hi), dbl = mt_desc_sw128(w_hi + (uint32_t)npad * 128u);
+            const int atoms = min(4, (kpad - c * MT_KC) >> 3);
+#pragma unroll 1
+            for (int j = 0; j < atoms; ++j) {
+              if (passes == 1 || p == 0) {
+                umma_tf32_elect(tacc, dal, dbh, idesc, acc);
+                umma_tf32_elect(tacc, dah, dbl, idesc, 1);
+                acc = 1;
+              }
+              if (passes == 1 || p == 1) umma_tf32_elect(tacc, dah, dbh, idesc, 1);
+              dah += 2; dal += 2; dbh += 2; dbl += 2;
+            }
+            umma_commit_elect(&Bq.wempty[s]);
+            umma_commit_elect(&Bq.aempty[ab]);
+            if (c == 0 && p == 0) MT_TRACE(1, blk * 26 + 6 + 6 * l);
           }
-          umma_commit_elect(&Bq.wempty[s]);
-          umma_commit_elect(&Bq.aempty[ab]);
         }
         umma_commit_elect(&Bq.accfull);
+        MT_TRACE(1, blk * 26 + 7 + 6 * l);
       }
     }
   } else {
     // ---------------- transform warps: thread = batch row = TMEM lane ----------------
-    const int grp = (warp - 2) >> 2;             // group g produces the operand chunks with (sequence number & 1) == g
+    const int xw = warp - 2;                     // 0..7
+    const int grp = xw >> 2;                     // group g produces the operand chunks with (sequence number & 1) == g
     const int quarter = warp & 3;                // TMEM lane quarter = warp id % 4
     const int r = quarter * 32 + lane;
     const int64_t b = b0 + r;
@@ -210,134 +240,226 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
     auto acquire = [&](uint32_t g) {   // operand buffer of production g is free: the MMAs of production g - 2 have read it
       mbar_wait(&Bq.aempty[g & 1], ((g >> 1) & 1) ^ 1);
     };
-    auto publish = [&](uint32_t g) {
+    auto publish = [&](uint32_t g) {   // this warp's rows of production g are in place
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&Bq.afull[g & 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&Bq.afull[g & 1]);
     };
     for (int blk = 0; blk < n_blocks; ++blk) {
       const MlpParams &P = blk ? P2.b : P2.a;
       const pcv_mlp_desc &d = P.d;
       const int k0pad = mt_pad16(P.n_in0);
       const int nch0 = mt_chunks(k0pad);
-      if (grp == 0) {
-        // ---- prologue: assemble x0 = [segments] (this thread: its own row), normalise, split, publish
+      MT_TRACE(0, blk * 26 + 0);
+      {
+        // ---- prologue: x0 = [segments] for the CTA's 128 rows.
+        // Pass 1 (all eight warps): warp w takes rows w, w + 8, ...; lane = element of the 32-wide chunk, so a lane's
+        // segment is fixed and its 16 rows' loads are independent: all of them are in flight together (two dependent
+        // round trips for a gather: index, then table row) instead of one round trip per element.
         if (blk > 0) {
-          // block b reads what block a's epilogue wrote for the same batch rows (z), possibly by another thread
+          // block b reads what block a's epilogue wrote for the same batch rows (z), by other threads of the CTA
           __threadfence_block();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         for (int c = 0; c < nch0; ++c) acquire(ga + c);
-        auto eaddr = [&](int e) {   // raw fp32 staging = the hi image of the chunk
-          const uint32_t kk = (uint32_t)e & 31u;
-          return abuf0 + ((ga + ((uint32_t)e >> 5)) & 1u) * MT_ABUF_BYTES + rowoff + ((((kk >> 2) ^ sw)) << 4) + ((kk & 3u) << 2);
-        };
-        for (int e = 0; e < nch0 * MT_KC; ++e) st_shared_f32(eaddr(e), 0.f);
-        if (b < B) {
-          for (int s = 0; s < d.n_segments; ++s) {
-            const pcv_segment &sg = d.seg[s];
-            const int off = P.seg_off[s];
-            if (sg.kind == PCV_SEG_DENSE) {
-              const float *src = (const float *)sg.ptr + b * sg.width;
-              for (int e = 0; e < sg.width; ++e) st_shared_f32(eaddr(off + e), __ldg(src + e));
-            } else if (sg.kind == PCV_SEG_ONEHOT) {
-              const float *rr = (const float *)sg.ptr + b * sg.count;
-              float sum = 0.f;
-              for (int l = 0; l < sg.count; ++l) sum += rr[l];
-              const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
-              if (hot >= 0 && hot <= sg.count) st_shared_f32(eaddr(off + hot), 1.f);
-            } else {  // GATHER
-              const float *tab = (const float *)sg.ptr;
-              const bool vec = (sg.width & 3) == 0 && ((reinterpret_cast<uintptr_t>(tab) & 15) == 0);
-              for (int c = 0; c < sg.count; ++c) {
-                const float *row = tab + sg.idx[b * sg.count + c] * (int64_t)sg.width;
-                const int e0 = off + c * sg.width;
-                if (vec) {
-                  for (int k = 0; k < sg.width; k += 4) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4 *>(row + k));
-                    st_shared_f32(eaddr(e0 + k), t4.x); st_shared_f32(eaddr(e0 + k + 1), t4.y);
-                    st_shared_f32(eaddr(e0 + k + 2), t4.z); st_shared_f32(eaddr(e0 + k + 3), t4.w);
-                  }
-                } else {
-                  for (int k = 0; k < sg.width; ++k) st_shared_f32(eaddr(e0 + k), __ldg(row + k));
+        MT_TRACE(0, blk * 26 + 1);
+        int oh_seg = -1;                   // the one-hot segment is filled by the row's own thread in pass 2
+        for (int s = 0; s < d.n_segments; ++s)
+          if (d.seg[s].kind == PCV_SEG_ONEHOT) oh_seg = s;
+        // this lane's element of chunk 0 and of chunk 1: segment kind, source pointers (both chunks' loads are issued
+        // before either is consumed)
+        int kind[2];
+        const float *src[2];
+        const int64_t *ip[2];
+        int64_t rs[2], is[2];              // row strides (floats / indices per batch row)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          kind[c] = -1; src[c] = nullptr; ip[c] = nullptr; rs[c] = 0; is[c] = 0;
+          const int e = c * MT_KC + lane;
+          if (c < nch0) {
+            for (int s = 0; s < d.n_segments; ++s) {
+              if (e >= P.seg_off[s] && e < P.seg_off[s + 1]) {
+                const pcv_segment &sg = d.seg[s];
+                const int le = e - P.seg_off[s];
+                kind[c] = sg.kind;
+                if (sg.kind == PCV_SEG_DENSE) {
+                  src[c] = (const float *)sg.ptr + le; rs[c] = sg.width;
+                } else if (sg.kind == PCV_SEG_GATHER) {
+                  const int which = le / sg.width;
+                  src[c] = (const float *)sg.ptr + (le - which * sg.width); rs[c] = sg.width;
+                  ip[c] = sg.idx + which; is[c] = sg.count;
                 }
               }
             }
           }
-          // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order as in mlp.cu
-          for (int s = 0; s < d.n_segments; ++s) {
-            if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
-            const int off = P.seg_off[s], w = P.seg_off[s + 1] - off;
-            float ss = 0.f;
-            for (int e = 0; e < w; ++e) { const float v = ld_shared_f32(eaddr(off + e)); ss = fmaf(v, v, ss); }
-            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-            for (int e = 0; e < w; ++e) st_shared_f32(eaddr(off + e), ld_shared_f32(eaddr(off + e)) / nrm);
-          }
-          if (d.copy_seg >= 0) {
-            const int off = P.seg_off[d.copy_seg], w = P.seg_off[d.copy_seg + 1] - off;
-            float *dst = d.out + b * d.out_ld;
-            for (int e = 0; e < w; ++e) dst[e] = ld_shared_f32(eaddr(off + e));
-          }
         }
-        for (int c = 0; c < nch0; ++c) {
-          const uint32_t base = abuf0 + ((ga + c) & 1u) * MT_ABUF_BYTES + rowoff;
+        if (blk == 0) MT_TRACE(0, 40);
+        float v[2][16];
+        int64_t gi[2][16];
 #pragma unroll
-          for (uint32_t u = 0; u < 8; ++u) {
-            const float4 x = ld_shared_v4(base + (u << 4));
-            mt_store_unit(base + (u << 4), x.x, x.y, x.z, x.w);
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int64_t bb = b0 + xw + 8 * k;
+            v[c][k] = 0.f;
+            gi[c][k] = -1;
+            if (bb < B) {
+              // dense: plain (coherent) loads — it may be what the previous block of this launch wrote
+              if (kind[c] == PCV_SEG_DENSE) v[c][k] = __ldcg(src[c] + bb * rs[c]);
+              else if (kind[c] == PCV_SEG_GATHER) gi[c][k] = __ldg(ip[c] + bb * is[c]);
+            }
+          }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (gi[c][k] >= 0) v[c][k] = __ldg(src[c] + gi[c][k] * rs[c]);
+        if (blk == 0) MT_TRACE(0, 41);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < nch0) {
+            const uint32_t base = abuf0 + ((ga + c) & 1u) * MT_ABUF_BYTES;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint32_t rr = (uint32_t)(xw + 8 * k);
+              st_shared_f32(base + rr * 128u + ((((uint32_t)lane >> 2) ^ (rr & 7u)) << 4) + (((uint32_t)lane & 3u) << 2), v[c][k]);
+            }
           }
         }
-        for (int c = 0; c < nch0; ++c) publish(ga + c);
+        // this row's click vector, requested before the barrier so its latency hides behind it
+        float rv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = 0.f;
+        if (grp == 0 && oh_seg >= 0 && b < B) {
+          const float *rr = (const float *)d.seg[oh_seg].ptr + b * d.seg[oh_seg].count;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < d.seg[oh_seg].count) rv[i] = __ldg(rr + i);
+        }
+        MT_TRACE(0, blk * 26 + 2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (blk == 0) MT_TRACE(0, 42);
+        if (grp == 0) {
+          // Pass 2 (thread = row): one-hot, normalise, HBM copies, split into tf32 hi | lo
+          auto eaddr = [&](int e) {   // raw fp32 staging = the hi image of the chunk
+            const uint32_t kk = (uint32_t)e & 31u;
+            return abuf0 + ((ga + ((uint32_t)e >> 5)) & 1u) * MT_ABUF_BYTES + rowoff + ((((kk >> 2) ^ sw)) << 4) + ((kk & 3u) << 2);
+          };
+          if (b < B) {
+            if (oh_seg >= 0) {
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum += rv[i];     // sequential order; + 0 for the padding
+              const int hot = (int)sum;  // .to(torch.long) truncates (cvae.py:91)
+              if (hot >= 0 && hot <= d.seg[oh_seg].count) st_shared_f32(eaddr(P.seg_off[oh_seg] + hot), 1.f);
+            }
+            // segment-wide L2 normalisation (F.normalize eps=1e-12), sequential sum order as in mlp.cu
+            for (int s = 0; s < d.n_segments; ++s) {
+              if (d.seg[s].norm != PCV_NORM_SEGMENT) continue;
+              const int off = P.seg_off[s], w = P.seg_off[s + 1] - off;
+              float ss = 0.f;
+              for (int e = 0; e < w; ++e) { const float x = ld_shared_f32(eaddr(off + e)); ss = fmaf(x, x, ss); }
+              const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+              for (int e = 0; e < w; ++e) st_shared_f32(eaddr(off + e), ld_shared_f32(eaddr(off + e)) / nrm);
+            }
+            if (blk == 0) MT_TRACE(0, 43);
+            if (d.copy_seg >= 0) {
+              const int off = P.seg_off[d.copy_seg], w = P.seg_off[d.copy_seg + 1] - off;
+              float *dst = d.out + b * d.out_ld;
+              for (int e = 0; e < w; ++e) dst[e] = ld_shared_f32(eaddr(off + e));
+            }
+          }
+          if (blk == 0) MT_TRACE(0, 44);
+          for (int c = 0; c < nch0; ++c) {
+            const uint32_t base = abuf0 + ((ga + c) & 1u) * MT_ABUF_BYTES + rowoff;
+#pragma unroll
+            float4 xs[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u) xs[u] = ld_shared_v4(base + ((u ^ sw) << 4));   // bank-conflict-free: rows differ in u ^ sw
+#pragma unroll
+            for (uint32_t u = 0; u < 8; ++u) {
+              const float4 x = xs[u];
+              const uint32_t o = (u ^ sw) << 4;
+              const uint32_t h0 = tf32_rna(x.x), h1 = tf32_rna(x.y), h2 = tf32_rna(x.z), h3 = tf32_rna(x.w);
+              st_shared_v4(base + o, h0, h1, h2, h3);
+              st_shared_v4(base + o + MT_AHALF_BYTES, tf32_rna(x.x - __uint_as_float(h0)), tf32_rna(x.y - __uint_as_float(h1)),
+                           tf32_rna(x.z - __uint_as_float(h2)), tf32_rna(x.w - __uint_as_float(h3)));
+            }
+          }
+          if (blk == 0) MT_TRACE(0, 45);
+          for (int c = 0; c < nch0; ++c) publish(ga + c);
+        }
+        MT_TRACE(0, blk * 26 + 3);
       }
       ga += nch0;
 
       for (int l = 0; l < d.n_layers; ++l, ++gl) {
         const pcv_linear &L = d.layer[l];
         const bool last = (l == d.n_layers - 1);
+        const int npad = mt_pad16(L.n_out);
+        const int nchn = mt_chunks(npad);
+        const int passes = last ? 1 : (npad > MT_TWOPASS_K ? 2 : 1);    // of the NEXT layer, whose operand this layer's output is
+        const float slope = L.act == PCV_ACT_LEAKY ? 0.01f : (L.act == PCV_ACT_RELU ? 0.f : 1.f);
         mbar_wait(&Bq.accfull, gl & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = lane_base + (gl & 1) * MT_MAXN;
+        MT_TRACE(0, blk * 26 + 4 + 6 * l);
         if (!last) {
-          const int nchn = mt_chunks(mt_pad16(L.n_out));
-          for (int c = 0; c < nchn; ++c) {
-            const uint32_t g = ga + c;
-            if ((int)(g & 1) != grp) continue;
-            acquire(g);
-            uint32_t v[32];
-            TC_LD32(v, tacc + (uint32_t)(c * MT_KC));
-            const int nb = c * MT_KC;
-            float bias[32];
+          for (int p = 0; p < passes; ++p) {
+            for (int c = 0; c < nchn; ++c) {
+              const uint32_t g = ga + (uint32_t)(p * nchn + c);
+              if ((int)(g & 1) != grp) continue;
+              const int nb = c * MT_KC;
+              float bias[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) bias[i] = (nb + i < L.n_out) ? __ldg(L.b + nb + i) : 0.f;
-            TC_WAIT_LD(v);
-            const uint32_t base = abuf0 + (g & 1u) * MT_ABUF_BYTES + rowoff;
+              for (int i = 0; i < 32; ++i) bias[i] = (nb + i < L.n_out) ? __ldg(L.b + nb + i) : 0.f;
+              const bool tr = (blk == 0 && l == 1 && c == 2 && p == 0);
+              if (tr) MT_TRACE(0, 50);
+              uint32_t v[32];
+              TC_LD32(v, tacc + (uint32_t)nb);
+              TC_WAIT_LD(v);
+              if (tr) MT_TRACE(0, 51);
+              float y[32];
 #pragma unroll
-            for (uint32_t u = 0; u < 8; ++u) {
-              float x[4];
+              for (int i = 0; i < 32; ++i) y[i] = mt_act(__uint_as_float(v[i]) + bias[i], slope);
+              if (tr) MT_TRACE(0, 52);
+              acquire(g);
+              if (tr) MT_TRACE(0, 53);
+              const uint32_t base = abuf0 + (g & 1u) * MT_ABUF_BYTES + rowoff;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) x[i] = apply_act(__uint_as_float(v[4 * u + i]) + bias[4 * u + i], L.act);
-              mt_store_unit(base + ((u ^ sw) << 4), x[0], x[1], x[2], x[3]);
+              for (uint32_t u = 0; u < 8; ++u) {
+                const uint32_t h0 = tf32_rna(y[4 * u]), h1 = tf32_rna(y[4 * u + 1]), h2 = tf32_rna(y[4 * u + 2]), h3 = tf32_rna(y[4 * u + 3]);
+                const uint32_t o = (u ^ sw) << 4;
+                st_shared_v4(base + o, h0, h1, h2, h3);
+                if (p == 0)     // the second pass (hi*hi) needs the hi image only
+                  st_shared_v4(base + o + MT_AHALF_BYTES, tf32_rna(y[4 * u] - __uint_as_float(h0)), tf32_rna(y[4 * u + 1] - __uint_as_float(h1)),
+                               tf32_rna(y[4 * u + 2] - __uint_as_float(h2)), tf32_rna(y[4 * u + 3] - __uint_as_float(h3)));
+              }
+              if (tr) MT_TRACE(0, 54);
+              publish(g);
+              if (tr) MT_TRACE(0, 55);
+              if (c < 2 && p == 0) MT_TRACE(0, blk * 26 + 5 + 6 * l + c);
             }
-            publish(g);
           }
-          ga += nchn;
+          ga += (uint32_t)(passes * nchn);
         } else if (grp == 0) {
           // ---- final epilogue: bias + activation -> out (+ reparameterisation)
-          const bool vec = b < B && ((d.out_ld | d.out_col0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+          const bool vec = ((d.out_ld | d.out_col0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
           float *orow = d.out + (b < B ? b : 0) * d.out_ld + d.out_col0;
           for (int nb = 0; nb < L.n_out; nb += 32) {
-            uint32_t v[32];
-            TC_LD32(v, tacc + (uint32_t)nb);
             float bias[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) bias[i] = (nb + i < L.n_out) ? __ldg(L.b + nb + i) : 0.f;
+            uint32_t v[32];
+            TC_LD32(v, tacc + (uint32_t)nb);
             TC_WAIT_LD(v);
             if (b < B) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float x[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = apply_act(__uint_as_float(v[i + j]) + bias[i + j], L.act);
+                for (int j = 0; j < 4; ++j) x[j] = mt_act(__uint_as_float(v[i + j]) + bias[i + j], slope);
                 if (vec && nb + i + 4 <= L.n_out) {
                   *reinterpret_cast<float4 *>(orow + nb + i) = make_float4(x[0], x[1], x[2], x[3]);
                 } else {
@@ -349,31 +471,48 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          MT_TRACE(0, blk * 26 + 22);
           if (d.latent > 0 && b < B) {
             // cvae.py:79-83: z = eps * exp(0.5 * logvar) + mu; this thread re-reads the [mu | logvar] row it just wrote
             const int Z = d.latent;
             const uint64_t rng_off = d.offset + (d.offset_dev ? *d.offset_dev : 0ull);
-            for (int j = 0; j < Z; ++j) {
-              const float mu = orow[j], lv = orow[Z + j];
-              float eps;
-              if (d.eps) {
-                eps = d.eps[b * Z + j];
-              } else {
-                float n4[4];
-                normal4(d.seed, rng_off, b, j >> 2, n4);
-                eps = n4[j & 3];
+            for (int j0 = 0; j0 < Z; j0 += 8) {      // batches of 8 latent columns: all loads first, then the stores
+              float mu[8], lv[8], ep[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const bool ok = j0 + i < Z;
+                mu[i] = ok ? __ldcg(orow + j0 + i) : 0.f;
+                lv[i] = ok ? __ldcg(orow + Z + j0 + i) : 0.f;
+                ep[i] = (ok && d.eps) ? __ldg(d.eps + b * Z + j0 + i) : 0.f;
               }
-              const float sd = pcv_expf(lv * 0.5f);
-              d.z[b * Z + j] = eps * sd + mu;
-              if (d.eps_out) d.eps_out[b * Z + j] = eps;
+              if (!d.eps) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                  float n4[4];
+                  normal4(d.seed, rng_off, b, (j0 + i) >> 2, n4);
+                  ep[i] = n4[0]; ep[i + 1] = n4[1]; ep[i + 2] = n4[2]; ep[i + 3] = n4[3];
+                }
+              }
+              float zz[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) zz[i] = ep[i] * pcv_expf(lv[i] * 0.5f) + mu[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (j0 + i < Z) {
+                  d.z[b * Z + j0 + i] = zz[i];
+                  if (d.eps_out) d.eps_out[b * Z + j0 + i] = ep[i];
+                }
             }
           }
+          MT_TRACE(0, blk * 26 + 23);
         }
       }
     }
+    MT_TRACE(0, 60);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  MT_TRACE(1, 63);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
@@ -383,6 +522,11 @@ mlp_tc_kernel(const __grid_constant__ MlpParams2 P2, int n_blocks, int64_t B) {
 bool mlp_tc_supported(const MlpParams *P) {
   const pcv_mlp_desc &d = P->d;
   if (P->n_in0 > MT_MAXK0 || d.x0 != nullptr) return false;
+  int n_onehot = 0;
+  for (int s = 0; s < d.n_segments; ++s)
+    if (d.seg[s].kind == PCV_SEG_ONEHOT) {
+      if (++n_onehot > 1 || d.seg[s].count > 16) return false;
+    }
   for (int l = 0; l < d.n_layers; ++l) {
     if (d.layer[l].Wt == nullptr || d.layer[l].n_out > MT_MAXN) return false;
     if (l < d.n_layers - 1 && d.acts[l] != nullptr) return false;
@@ -421,6 +565,12 @@ int mlp_tc_launch(const MlpParams *Pa, const MlpParams *Pb, int64_t B, cudaStrea
 using namespace pcv;
 
 extern "C" {
+
+#ifdef PCV_TC_TRACE
+int pcv_debug_mlp_tc_trace(long long *host) {
+  return (int)cudaMemcpyFromSymbol(host, g_mt_trace, sizeof(long long) * 2 * 64);
+}
+#endif
 
 size_t pcv_mlp_tc_packed_bytes(int n_in, int n_out) {
   if (n_in <= 0 || n_out <= 0) return 0;

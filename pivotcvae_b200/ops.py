@@ -395,18 +395,21 @@ def repack_stale():
 
 PACK_WEIGHTS = True   # False: always stream nn.Linear weights as they are (the training engine)
 # Inference engine of the fused MLP blocks: "exact" = the FFMA engines (sequential-k FMA chain, bit-identical to the
-# CPU oracle); "tc" = the tcgen05 3xTF32 engine (csrc/mlp_tc.cu: fp32-grade, ~1e-6 of torch's addmm, several times
-# faster) wherever a block fits it (input <= 64 wide, layers <= 256 wide), the exact engines elsewhere.
+# CPU oracle); "tc" = the tcgen05 3xTF32 engine (csrc/mlp_tc.cu: fp32-grade, ~1e-6 of torch's addmm) wherever a block
+# fits it (input <= 64 wide, layers <= 256 wide), the exact engines elsewhere; "auto" = "tc" for batches of at least
+# TC_MIN_ROWS rows (a tcgen05 CTA owns 128 rows and takes ~30 us per block whatever the batch, the FFMA engine spreads
+# 1024 rows over 128 CTAs in ~18 us but needs ~50 us at 4096 rows and ~180 us at 16384), "exact" below.
 MLP_ENGINE = "exact"
 TC_MAX_IN, TC_MAX_WIDTH = 64, 256
+TC_MIN_ROWS = 2048
 
 
 class mlp_engine:
     """Context manager: `with ops.mlp_engine("tc"): ...`"""
 
     def __init__(self, name):
-        if name not in ("exact", "tc"):
-            raise ValueError("mlp engine must be 'exact' or 'tc'")
+        if name not in ("exact", "tc", "auto"):
+            raise ValueError("mlp engine must be 'exact', 'tc' or 'auto'")
         self.name = name
 
     def __enter__(self):
@@ -430,9 +433,9 @@ def _mlp_desc(segments, layers, B, *, out=None, out_ld=None, out_col0=0, copy_se
         s.fill(d.seg[i], keep)
     n_in0 = sum(s.width for s in segments)
     engine = engine or MLP_ENGINE
-    if engine not in ("exact", "tc"):
-        raise ValueError("mlp engine must be 'exact' or 'tc'")
-    tc = (engine == "tc" and not save and PACK_WEIGHTS and n_in0 <= TC_MAX_IN
+    if engine not in ("exact", "tc", "auto"):
+        raise ValueError("mlp engine must be 'exact', 'tc' or 'auto'")
+    tc = ((engine == "tc" or (engine == "auto" and B >= TC_MIN_ROWS)) and not save and PACK_WEIGHTS and n_in0 <= TC_MAX_IN
           and all(W.shape[0] <= TC_MAX_WIDTH for W, _, _ in layers))
     d.n_layers = len(layers)
     prev = n_in0

@@ -105,6 +105,33 @@ def p_mlp():         # mlp_cluster_kernel: prior->z->PSM chain, SCM, response ML
     timed("recommend+resp B=4096 (100k)", step, 4096 * 564 / 1e3, "TB/s (algorithmic)")
 
 
+def p_mlp_engines():  # every MLP block of a C4 / C2 step alone, FFMA cluster engine vs the tcgen05 engine (mlp_tc_kernel)
+    for B in (512, 1024, 4096, 16384):
+        env, model, users, ctx = _models(100000, 100000, 5, B)
+        items = torch.randint(0, 100000, (B, 5), generator=G, device=DEV)
+        pivot = torch.randint(0, 100000, (B,), generator=G, device=DEV)
+        with torch.no_grad():
+            r, u, _ = model._inputs(ctx, users)
+            _, z, _ = model._prior_chain(r, u, model.psmMLP)
+            blocks = {"prior->z->PSM chain": lambda: model._prior_chain(r, u, model.psmMLP),
+                      "SCM": lambda: model._scm(z, ("onehot", r), pivot, model._user_seg(u), []),
+                      "response MLP": lambda: env(items, users)}
+            flops = {"prior->z->PSM chain": 2 * (14 * 128 + 128 * 128 + 128 * 32 + 30 * 256 + 256 * 256 + 256 * 8),
+                     "SCM": 2 * (38 * 256 + 256 * 256 + 256 * 32), "response MLP": 2 * (48 * 256 + 256 * 256 + 256 * 5)}
+            for eng in ("exact", "tc"):
+                with ops.mlp_engine(eng):
+                    for name, fn in blocks.items():
+                        # 20 launches per graph replay: the eager call is launch-bound (~60-90 us of Python per call)
+                        fn()
+                        torch.cuda.synchronize()
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr):
+                            for _ in range(20):
+                                fn()
+                        timed("%-20s B=%-5d %-5s x20" % (name, B, eng), gr.replay, 20 * B * flops[name] / 1e9, "TFLOP/s", iters=5)
+                        del gr
+
+
 def p_respmlp():     # response MLP alone at a gather-bound batch
     env, model, users, ctx = _models(1000000, 1000000, 5, 65536)
     slates = torch.randint(0, 1000000, (65536, 5), generator=G, device=DEV)

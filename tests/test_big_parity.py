@@ -203,6 +203,58 @@ def test_gpu_greedy_slates_at_baseline_sizes(name, tag, engine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,tag", [("c2", "greedy_k3/"), ("c2", "greedy_k10/"), ("c4", "greedy_k2/")])
+def test_gpu_tc_mlp_engine_slates_at_baseline_sizes(name, tag):
+    """The tcgen05 engine of the MLP blocks (mlp_engine="tc": 3xTF32, fp32-grade but not bit-identical to the FMA
+    chain) against the UNMODIFIED reference at the BASELINE sizes: every slot audited, a mismatch is accepted only if
+    the reference's own top1-top2 gap is below the measured |dq| |w| (audit_slates), z_mu / rx within 1e-4."""
+    from gpu_util import N, T
+    from pivotcvae_b200 import ops
+    fx = big(name)
+    w, sd, env_sd, m, env = _gpu_model(name, "pivot", fx)
+    m.mlp_engine = env.mlp_engine = "tc"
+    B = int(fx["B"])
+    ctx = T(synth.contexts(B, w["L"], int(fx[tag + "k"])))
+    users = None if w["no_user"] else T(fx["users"])
+    m.noise.push("eps", T(fx[tag + "eps"]))
+    items, z_mu = m.recommend(ctx, users, return_item=True)          # the public call
+    with ops.mlp_engine("tc"):
+        m.noise.push("eps", T(fx[tag + "eps"]))
+        items2, z_mu2, rx, pidx, pivot_out = _pivot_pieces(m, ctx, users)
+    assert torch.equal(items, items2)
+    m.mlp_engine = None
+    m.noise.push("eps", T(fx[tag + "eps"]))
+    rx_exact, _ = m.recommend(ctx, users, return_item=False)
+    assert not torch.equal(rx.view(-1), rx_exact.reshape(-1))        # the tc engine really ran
+    e = audit_slates("gpu-mlp-tc/%s/%s" % (name, tag[:-1]), fx, tag, w, N(items), N(rx), N(pidx), N(pivot_out))
+    assert e["unexplained"] == 0
+    np.testing.assert_allclose(N(z_mu), fx[tag + "z_mu"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N(rx).reshape(-1), fx[tag + "rx"].reshape(-1), rtol=1e-4, atol=1e-5)
+    if name == "c2" and tag == "greedy_k3/":
+        resp = env(items.view(B, -1), T(fx["users"]))
+        if e["pivot_flips"] == 0 and e["slot_mismatches"] == 0:
+            np.testing.assert_allclose(N(resp), fx[tag + "resp"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_tc_mlp_engine_list_slates_c2():
+    from gpu_util import N, T
+    fx = big("c2")
+    w, sd, env_sd, m, env = _gpu_model("c2", "list", fx, prefix="list/")
+    m.mlp_engine = "tc"
+    lfx = {k[5:]: v for k, v in fx.items() if k.startswith("list/")}
+    B, tag = int(fx["B"]), "list_k4/"
+    ctx = T(synth.contexts(B, w["L"], int(lfx[tag + "k"])))
+    m.noise.push("eps", T(lfx[tag + "eps"]))
+    items, z_mu = m.recommend(ctx, None, return_item=True)
+    m.noise.push("eps", T(lfx[tag + "eps"]))
+    rx, _ = m.recommend(ctx, None, return_item=False)
+    e = audit_slates("gpu-mlp-tc/c2/list_k4", lfx, tag, w, N(items), N(rx))
+    assert e["unexplained"] == 0
+    np.testing.assert_allclose(N(z_mu), lfx[tag + "z_mu"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
 def test_gpu_sampled_slates_c2_identical_rng():
     from gpu_util import N, T
     fx = big("c2")
