@@ -767,19 +767,20 @@ def run_ours(args, w):
                     also.append(r)
                 except Exception as e:     # noqa: BLE001
                     also.append({"workload": wn, "mode": "train", "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
-            if args.mlp_engine == "exact":
-                # the same headline config with the tcgen05 engine of the MLP blocks (csrc/mlp_tc.cu: fp32-grade, not
-                # bit-identical to the FMA chain, hence not the headline)
-                try:
-                    args.mlp_engine = "tc"
-                    r, _ = measure_generate(D, args, args.workload, args.mode, 0.25, cpu_seconds=0)
-                    also.append({"workload": args.workload, "mode": args.mode, "mlp_engine": "tc", "value": r["value"], "unit": r["unit"],
-                                 "ms_per_step": r["ms_per_step"], "parity_check": r.get("parity_check"),
-                                 "parity_detail": r.get("parity_detail"), "per_call_ms": r.get("roofline", {}).get("per_call_ms")})
-                except Exception as e:     # noqa: BLE001
-                    also.append({"workload": args.workload, "mode": args.mode, "mlp_engine": "tc", "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
-                finally:
-                    args.mlp_engine = "exact"
+            # the same headline config with the other engine of the MLP blocks: FFMA chain (bit-identical to the oracle) vs
+            # tcgen05 3xTF32 (csrc/mlp_tc.cu: fp32-grade, gated on the reference fixtures and the parity check below)
+            other = "tc" if args.mlp_engine == "exact" else "exact"
+            saved_engine = args.mlp_engine
+            try:
+                args.mlp_engine = other
+                r, _ = measure_generate(D, args, args.workload, args.mode, 0.25, cpu_seconds=0)
+                also.append({"workload": args.workload, "mode": args.mode, "mlp_engine": other, "value": r["value"], "unit": r["unit"],
+                             "ms_per_step": r["ms_per_step"], "parity_check": r.get("parity_check"),
+                             "parity_detail": r.get("parity_detail"), "per_call_ms": r.get("roofline", {}).get("per_call_ms")})
+            except Exception as e:     # noqa: BLE001
+                also.append({"workload": args.workload, "mode": args.mode, "mlp_engine": other, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
+            finally:
+                args.mlp_engine = saved_engine
             extra["also"] = also
     D.stop()
     if D.rank != 0:
@@ -820,7 +821,7 @@ def main():
     ap.add_argument("--ce-engine", default="tf32", choices=["exact", "tf32"],
                     help="train mode, full catalog: CE logits in exact fp32 (SIMT) or tf32 on the tensor cores (C3 is a reduced-precision config)")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
-    ap.add_argument("--mlp-engine", default="exact", choices=["exact", "tc", "auto"],
+    ap.add_argument("--mlp-engine", default="auto", choices=["exact", "tc", "auto"],
                     help="fused MLP blocks at inference: tc = tcgen05 3xTF32 (fp32-grade), exact = FFMA chain bit-identical to the oracle, "
                          "auto = tc for batches of >= 2048 rows")
     ap.add_argument("--batch", type=int, default=0)

@@ -132,6 +132,24 @@ def p_mlp_engines():  # every MLP block of a C4 / C2 step alone, FFMA cluster en
                         del gr
 
 
+def p_mlp_tc():      # mlp_tc_kernel (tcgen05 3xTF32, two-pass): the same three blocks of a C4 step, B = 4096, 20 launches per graph
+    B = 4096
+    env, model, users, ctx = _models(100000, 100000, 5, B)
+    items = torch.randint(0, 100000, (B, 5), generator=G, device=DEV)
+    pivot = torch.randint(0, 100000, (B,), generator=G, device=DEV)
+    flops = 2 * (14 * 128 + 128 * 128 + 128 * 32 + 30 * 256 + 256 * 256 + 256 * 8) + 2 * (38 * 256 + 256 * 256 + 256 * 32) + \
+        2 * (48 * 256 + 256 * 256 + 256 * 5)
+    with torch.no_grad(), ops.mlp_engine("tc"):
+        r, u, _ = model._inputs(ctx, users)
+        _, z, _ = model._prior_chain(r, u, model.psmMLP)
+
+        def step():
+            model._prior_chain(r, u, model.psmMLP)
+            model._scm(z, ("onehot", r), pivot, model._user_seg(u), [])
+            env(items, users)
+        timed("MLP blocks tc B=4096 (3 launches)", step, B * flops / 1e9, "TFLOP/s (fp32-equivalent flops)")
+
+
 def p_respmlp():     # response MLP alone at a gather-bound batch
     env, model, users, ctx = _models(1000000, 1000000, 5, 65536)
     slates = torch.randint(0, 1000000, (65536, 5), generator=G, device=DEV)
