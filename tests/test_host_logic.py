@@ -241,3 +241,21 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     assert line["config"] == {"workload": line["config"]["workload"], "batch": 64, "mode": "greedy", "model": "PivotCVAE gt_pi"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "slates/s"
+
+
+def test_mlp_engine_policy_is_validated_and_scoped():
+    """ops.mlp_engine: context manager over the process default; unknown names are rejected; the library default is the
+    bit-exact FFMA engine and the model classes default to it (mlp_engine = None)."""
+    from pivotcvae_b200 import ops
+    from pivotcvae_b200.models.cvae import BaseCVAE
+    from pivotcvae_b200.env.response_model import UserResponseModel_MLP
+    assert ops.MLP_ENGINE == "exact" and BaseCVAE.mlp_engine is None and UserResponseModel_MLP.mlp_engine is None
+    with ops.mlp_engine("tc"):
+        assert ops.MLP_ENGINE == "tc"
+        with ops.mlp_engine("auto"):
+            assert ops.MLP_ENGINE == "auto"
+        assert ops.MLP_ENGINE == "tc"
+    assert ops.MLP_ENGINE == "exact"
+    with pytest.raises(ValueError):
+        ops.mlp_engine("bf16")
+    assert ops.TC_MAX_IN == 64 and ops.TC_MAX_WIDTH == 256 and ops.TC_MIN_ROWS >= 1024
