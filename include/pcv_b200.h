@@ -78,6 +78,8 @@ int pcv_normalize_rows(const float *W, int64_t n_rows, int dim, float *out,
 #define PCV_ENGINE_AUTO 0
 #define PCV_ENGINE_SIMT 1    /* exact fp32 FMA chain on CUDA cores                  */
 #define PCV_ENGINE_TCGEN05 2 /* tf32 tcgen05 filter + exact fp32 refine (greedy)    */
+#define PCV_ENGINE_TCGEN05_F16 3 /* dim 8: f16 tcgen05 filter (f16 accumulators read two per register, packed 16-bit
+                                  * maxima) + the same exact fp32 refine: identical results                           */
 
 typedef struct {
   int mode;           /* PCV_SELECT_*                                              */

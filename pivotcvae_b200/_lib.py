@@ -18,7 +18,7 @@ ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 SEG_DENSE, SEG_ONEHOT, SEG_GATHER = 0, 1, 2
 NORM_NONE, NORM_SEGMENT = 0, 1
 SELECT_GREEDY, SELECT_EXPRACE = 0, 1
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_F16 = 0, 1, 2, 3
 URM, URM_P, URM_P_MR = 0, 1, 2
 
 c_void_p, c_int, c_int64, c_uint64, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,

@@ -110,6 +110,7 @@ int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset
   t->tmap_valid = 0;
   t->packed = nullptr;
   t->packed_t = nullptr;
+  t->packed_h = nullptr;
   cudaGetDevice(&t->device);
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, t->device);
   // one-off: max row norm (error bound of the tf32 filter) + TMA descriptor

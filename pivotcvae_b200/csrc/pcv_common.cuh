@@ -25,6 +25,7 @@ struct Table {
   // tcgen05 path: pre-swizzled (SWIZZLE_32B image) copy of W owned by the handle
   float *packed;
   float *packed_t;   // transposed per-tile image for the CE gradient MMA (ce_tc2.cu), built on first use
+  void *packed_h;    // D = 8: f16 image (8 dims + constant dimension, SWIZZLE_32B) for the f16 filter (score_select_tc.cu)
   int tmap_valid;  // 1 when the tcgen05 engine can serve this table
   float max_row_norm;  // max_j |w_j|_2 (error bound of the tf32 filter)
   int tc_chunk_tiles;  // tcgen05 filter: tiles per column chunk once the table outgrows the L2

@@ -366,9 +366,10 @@ void launch_select_finalize(const float *pv, const int32_t *pi, int n_parts, int
 
 // tcgen05 engine (score_select_tc.cu)
 int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val,
-                    void *ws, size_t ws_bytes, cudaStream_t st);
+                    void *ws, size_t ws_bytes, cudaStream_t st, int f16);
 size_t score_select_tc_workspace(const Table *t, int64_t M);
 bool score_select_tc_supported(const Table *t);
+bool score_select_tc_f16_supported(const Table *t);
 
 }  // namespace pcv
 
@@ -429,12 +430,12 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
   if (engine == PCV_ENGINE_AUTO)  // tensor cores whenever the shape allows and the catalog is not tiny
     engine = (opts->mode == PCV_SELECT_GREEDY && score_select_tc_supported(t) && t->n_rows >= 2048)
                  ? PCV_ENGINE_TCGEN05 : PCV_ENGINE_SIMT;
-  if (engine == PCV_ENGINE_TCGEN05) {
+  if (engine == PCV_ENGINE_TCGEN05 || engine == PCV_ENGINE_TCGEN05_F16) {
     if (opts->mode != PCV_SELECT_GREEDY || !score_select_tc_supported(t)) {
       set_error("score_select: tcgen05 engine needs greedy mode and dim 8, 16, 32, 64 or 128 (dim %d, mode %d)", t->dim, opts->mode);
       return PCV_ERR_UNSUPPORTED;
     }
-    return score_select_tc(t, Q, M, out_idx, out_val, workspace, workspace_bytes, st);
+    return score_select_tc(t, Q, M, out_idx, out_val, workspace, workspace_bytes, st, engine == PCV_ENGINE_TCGEN05_F16);
   }
 
   SSPlan p;

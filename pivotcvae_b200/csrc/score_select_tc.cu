@@ -33,6 +33,7 @@
 // (streams whose overflow region is full too are flagged and scanned exactly by the
 // refine kernel).
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -123,6 +124,57 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[1
   return max3(max3(a, b, c), g[9], g[10]);
 }
 
+// ---- f16 filter (D = 8): kind::f16 MMA with f16 accumulators.  An f16 accumulator occupies one 32-bit TMEM column
+// (low half), but tcgen05.ld ... .pack::16b returns two columns per register at twice the fp32 element rate
+// (profiles/micro/tmem_f16.cu: 142 vs 277 cycles per 128 x 256 tile), and VIMNMX3.U16x2 takes the maximum of SIX
+// 16-bit values per instruction — IF the approximate scores are non-negative, so that their f16 bit patterns order
+// like unsigned integers.  kind::f16 has K = 16 and D = 8 uses half of it: dimension 8 carries a constant,
+// q'_8 = w_8 = 1, and the query row is scaled by a power of two so that |q'| max|w| is in [0.5, 0.997]:
+//     a~ = sum_k f16(q'_k) f16(w_k) + 1   in (0, 2),   |a~ - (s' + 1)| <= 2^-10 (operands, RN) + 2^-10 (result) = 2^-9.
+// Scaling a row by 2^-e does not move its arg-max, so the filter runs entirely in that scaled, shifted domain with the
+// CONSTANT band 2 * 1.25 * 2^-9; the refine re-scores the surviving chunks with the exact fp32 chain as before.
+constexpr float TC_H_BAND = 2.0f * 1.25f * 0.001953125f;
+constexpr uint32_t TC_IDESC_F16 = (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 64 TMEM columns of f16 accumulators -> 32 registers of two (column 2i in the low half, 2i + 1 in the high half)
+#define TC_LD32_PACK16(v, taddr)                                                                            \
+  asm volatile(                                                                                             \
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "                                                   \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"             \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),            \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),          \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),          \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                               \
+      : "r"(taddr))
+// packed unsigned maximum of 16 registers (32 values): 7 VIMNMX3.U16x2 -> two registers whose maximum is the chunk's
+__device__ __forceinline__ void chunk_max_u16x2(const uint32_t *v, uint32_t &b0, uint32_t &b1) {
+  const uint32_t a0 = __vimax3_u16x2(v[0], v[1], v[2]), a1 = __vimax3_u16x2(v[3], v[4], v[5]);
+  const uint32_t a2 = __vimax3_u16x2(v[6], v[7], v[8]), a3 = __vimax3_u16x2(v[9], v[10], v[11]);
+  const uint32_t a4 = __vimax3_u16x2(v[12], v[13], v[14]);
+  b0 = __vimax3_u16x2(a0, a1, a2);
+  b1 = __vimax3_u16x2(a3, a4, v[15]);
+}
+// power-of-two scale of a query row of the f16 filter: |q| wmax 2^-e in [0.5, 1) with wmax inflated by 0.3 %
+__device__ __forceinline__ float tc_h_scale(float ss, float wmax_s) {
+  const float t = sqrtf(ss) * wmax_s;
+  if (!(t > 0.f) || !(t < 3.0e38f)) return 1.f;      // zero / non-finite row: every approximate score is the constant
+  int e;
+  frexpf(t, &e);
+  e = max(-100, min(100, e));
+  return ldexpf(1.f, -e);
+}
+
 // Packed exact winner of a row among its overflow chunks, merged with a 64-bit atomicMax:
 // (order-preserving float bits << 32) | (0xffffffff - item) -> largest score, then lowest index.
 __device__ __forceinline__ unsigned long long pack_best(float v, int32_t j) {
@@ -193,15 +245,16 @@ __host__ __device__ __forceinline__ int tc_cta_of(int64_t x, int64_t n_units, in
 //             then lane 0 streams that item's table tiles with TMA bulk copies;
 //   warp 1  : lane 0 issues one tcgen05.mma per tile (TMEM alloc/dealloc by the whole warp);
 //   warps 2+: epilogue (thread = query row x column slice).
-template <int KA>
+template <int KA, bool F16 = false>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ W, int64_t n_rows,
                        const float *__restrict__ Q, int64_t M, int T, int Tc, int row_tiles, int slots_max,
-                       float band_scale, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
+                       float band_scale /* F16: max|w| * 1.003 */, float *__restrict__ out_r, int32_t *__restrict__ out_cnt,
                        unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                        unsigned long long *__restrict__ ovf_ent, int32_t *__restrict__ ovf_row, unsigned int ovf_cta_cap) {
   using C = TcCfg<KA>;
   constexpr int D = C::D;
+  static_assert(!F16 || KA == 1, "the f16 filter is built for D = 8");
   extern __shared__ unsigned char smem_raw[];
   TcSmem<KA> &S = *reinterpret_cast<TcSmem<KA> *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -273,6 +326,18 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
               q0 = __ldg(reinterpret_cast<const float4 *>(Q + row * D + a * 8));
               q1 = __ldg(reinterpret_cast<const float4 *>(Q + row * D + a * 8) + 1);
             }
+            if constexpr (F16) {
+              // 16 f16 per row: the 8 scaled dimensions, then the constant dimension (1 for live rows) and zeros
+              float ss = 0.f;
+              ss = fmaf(q0.x, q0.x, ss); ss = fmaf(q0.y, q0.y, ss); ss = fmaf(q0.z, q0.z, ss); ss = fmaf(q0.w, q0.w, ss);
+              ss = fmaf(q1.x, q1.x, ss); ss = fmaf(q1.y, q1.y, ss); ss = fmaf(q1.z, q1.z, ss); ss = fmaf(q1.w, q1.w, ss);
+              const float sc = tc_h_scale(ss, band_scale);
+              const __half2 h0 = __floats2half2_rn(q0.x * sc, q0.y * sc), h1 = __floats2half2_rn(q0.z * sc, q0.w * sc);
+              const __half2 h2 = __floats2half2_rn(q1.x * sc, q1.y * sc), h3 = __floats2half2_rn(q1.z * sc, q1.w * sc);
+              q0 = make_float4(__uint_as_float(*reinterpret_cast<const uint32_t *>(&h0)), __uint_as_float(*reinterpret_cast<const uint32_t *>(&h1)),
+                               __uint_as_float(*reinterpret_cast<const uint32_t *>(&h2)), __uint_as_float(*reinterpret_cast<const uint32_t *>(&h3)));
+              q1 = make_float4(__uint_as_float(row < M ? 0x00003C00u : 0u), 0.f, 0.f, 0.f);
+            }
             float4 *dst = reinterpret_cast<float4 *>(S.a[ab] + a * C::ATOM_A + t * 8);
             dst[0 ^ sw] = q0;
             dst[1 ^ sw] = q1;
@@ -336,9 +401,13 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
             if (gt == 0) TC_TRACE(4);
             // one k-step (8 fp32 = 32 B) per k-atom: the descriptors step by whole atoms (4 KB of A, 8 KB of B)
 #pragma unroll
-            for (int a = 0; a < C::KS; ++a)
-              umma_tf32_elect(tmem + buf * TC_BN, adesc + (uint64_t)(((kg * C::KS + a) * C::ATOM_A * 4) >> 4),
-                              umma_desc_sw32(S.b[s] + a * C::ATOM_B), TC_IDESC, (kg | a) != 0);
+            for (int a = 0; a < C::KS; ++a) {
+              if constexpr (F16)
+                umma_f16_elect(tmem + buf * TC_BN, adesc, umma_desc_sw32(S.b[s]), TC_IDESC_F16, 0);
+              else
+                umma_tf32_elect(tmem + buf * TC_BN, adesc + (uint64_t)(((kg * C::KS + a) * C::ATOM_A * 4) >> 4),
+                                umma_desc_sw32(S.b[s] + a * C::ATOM_B), TC_IDESC, (kg | a) != 0);
+            }
             umma_commit_elect(&S.empty[s]);
           }
           umma_commit_elect(&S.tfull[buf]);
@@ -360,6 +429,15 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
     asm volatile("mov.u32 %0, %1;" : "=r"(taddr0) : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slice * SEL_SW)));
     uint32_t gt = 0;
     float r = 0.f, thr = 0.f, band = 0.f;   // per-row state of the current segment
+    uint32_t thrm2 = 0u;                    // F16: (f16 bits of thr rounded down) - 1 in both halves: a chunk passes iff some value > it
+    auto pack_thr = [&]() {
+      if constexpr (F16) {
+        uint32_t t16 = 0u;
+        if (thr > 0.f) t16 = (uint32_t)__half_as_ushort(__float2half_rd(thr));   // +inf (dummy rows) -> 0x7C00: nothing passes
+        const uint32_t tm = t16 ? t16 - 1u : 0u;
+        thrm2 = tm * 0x10001u;
+      }
+    };
     for (int ch = 0; ch < n_chunks; ++ch) {
     TC_CHUNK(ch)
     for (int64_t u = u_begin; u < u_end;) {
@@ -368,13 +446,18 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
       const int64_t row = (int64_t)rt * TC_BM + trow;
       const bool live = row < M;
       {   // every segment starts on new rows: reset the running max
-        float ss = 0.f;
-        if (live) ss = tc_norm2<D>(Q + row * D);
-        band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
+        if constexpr (F16) {
+          band = TC_H_BAND;     // constant in the scaled, shifted domain of the approximate scores
+        } else {
+          float ss = 0.f;
+          if (live) ss = tc_norm2<D>(Q + row * D);
+          band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
+        }
         // running max of the approximate scores; finite start so that masked (-inf) columns
         // never pass, +inf for dummy rows so that nothing ever passes
         r = live ? -3.0e38f : INFINITY;
         thr = r;
+        pack_thr();
         atomicExch(reinterpret_cast<unsigned int *>(&S.rmax[trow]), __float_as_uint(-3.0e38f));   // shared with the other column slices
       }
       int cnt = 0;
@@ -412,6 +495,26 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
           }
         }
       };
+      // f16 filter: 32 items = 16 packed registers; 7 VIMNMX3.U16x2 + one against the packed threshold
+      auto process_h = [&](const uint32_t *v, int32_t jb) {
+        uint32_t b0, b1;
+        chunk_max_u16x2(v, b0, b1);
+        if (__vimax3_u16x2(b0, b1, thrm2) != thrm2) {     // some approximate score >= f16(thr)
+          const uint32_t bm = __vmaxu2(b0, b1);
+          const uint32_t m16 = max(bm & 0xffffu, bm >> 16);
+          const float m = __half2float(__ushort_as_half((unsigned short)m16));
+          r = fmaxf(r, m);
+          thr = r - band;
+          pack_thr();
+          if (cnt == C::CAP) compact();
+          if (cnt < C::CAP) {
+            list[cnt * TC_BM] = ((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb;
+            ++cnt;
+          } else {
+            spill(((unsigned long long)__float_as_uint(m) << 32) | (uint32_t)jb);
+          }
+        }
+      };
       auto mask_tail = [&](uint32_t (&v)[32], int col0, int n_valid) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -432,7 +535,9 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         const uint32_t taddr = taddr0 + buf * TC_BN;
         uint32_t va[32], vb[32];
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
-        TC_LD32(va, taddr);
+        // (f16 filter: ONE packed load brings the slice's 64 columns)
+        if constexpr (F16) TC_LD32_PACK16(va, taddr);
+        else TC_LD32(va, taddr);
         // (first tiles of a long segment, while the TMEM load is in flight) exchange the running max with the
         // other column slices.  The slices are never more than the two TMEM buffers apart, so with >= 8 tiles
         // per exchanging segment a slice can not read a value another one published for a LATER segment.
@@ -441,10 +546,23 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
           const float sh = (r >= 0.f)
               ? __int_as_float(atomicMax(reinterpret_cast<int *>(&S.rmax[trow]), __float_as_int(r)))
               : __uint_as_float(atomicMin(reinterpret_cast<unsigned int *>(&S.rmax[trow]), __float_as_uint(r)));
-          if (sh > r) { r = sh; thr = r - band; }
+          if (sh > r) { r = sh; thr = r - band; pack_thr(); }
         }
         TC_WAIT_LD(va);
-        if (t < n_full) {
+        if constexpr (F16) {
+          static_assert(SEL_SW == 64, "one packed load per slice");
+          (void)vb;
+          if (t >= n_full) {   // last tile of the table: columns beyond its end (stale ring data) -> 0, below every live score
+            const int n_valid = (int)min((int64_t)SEL_SW, j_end - (int64_t)jb0);  // may be <= 0
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (2 * i >= n_valid) va[i] &= 0xffff0000u;
+              if (2 * i + 1 >= n_valid) va[i] &= 0x0000ffffu;
+            }
+          }
+          process_h(va, jb0);
+          process_h(va + 16, jb0 + 32);
+        } else if (t < n_full) {
 #pragma unroll
           for (int c = 0; c < NCH; c += 2) {
             TC_LD32(vb, taddr + (c + 1) * 32);
@@ -527,7 +645,7 @@ extern "C" int pcv_debug_tc_cta(long long *host4x256) {
 template <int D>
 __global__ void __launch_bounds__(256, D <= 16 ? 5 : 4)
 tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset, const float *__restrict__ Q,
-                 int64_t M, int T, int Tc, int row_tiles, int slots_max, int G, float band_scale,
+                 int64_t M, int T, int Tc, int row_tiles, int slots_max, int G, float band_scale, float band_const,
                  const float *__restrict__ out_r, const int32_t *__restrict__ out_cnt,
                  const unsigned long long *__restrict__ out_ent, unsigned long long *__restrict__ row_best,
                  unsigned int *__restrict__ ovf_count_reset, int64_t *__restrict__ out_idx,
@@ -585,7 +703,9 @@ tc_refine_kernel(const float *__restrict__ W, int64_t n_rows, int64_t row_offset
   } else {
     ss = tc_norm2<D>(Q + row * D);
   }
-  const float band = band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
+  // (f16 filter: the running maxima and the recorded approximate maxima live in the scaled, shifted domain of that
+  // filter, where the band is a constant)
+  const float band = band_const > 0.f ? band_const : band_scale * sqrtf(ss) * 1.0001f + 1e-37f;
   R = warp_max(R);
   const float thr = R - band;
   float best = -INFINITY;
@@ -733,9 +853,26 @@ __global__ void pack_sw32_kernel(const float4 *__restrict__ W, int64_t n_rows, i
   out[((j >> 8) * ka + a) * (TC_BN * 2) + (j & (TC_BN - 1)) * 2 + (c ^ (int)((j >> 2) & 1))] = W[f];
 }
 
+// f16 image of a D = 8 table for the f16 filter: row j = 16 f16 (8 dimensions, then the constant dimension 1 and zeros)
+// = 32 B, the two 16-byte halves swapped when bit 2 of the row index is set (the same SWIZZLE_32B rule)
+__global__ void pack_h16_kernel(const float4 *__restrict__ W, int64_t n_rows, uint4 *__restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_rows) return;
+  const float4 w0 = W[2 * j], w1 = W[2 * j + 1];
+  const __half2 h0 = __floats2half2_rn(w0.x, w0.y), h1 = __floats2half2_rn(w0.z, w0.w);
+  const __half2 h2 = __floats2half2_rn(w1.x, w1.y), h3 = __floats2half2_rn(w1.z, w1.w);
+  const uint4 lo = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                              *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+  const uint4 hi = make_uint4(0x00003C00u, 0u, 0u, 0u);
+  const int sw = (int)((j >> 2) & 1);
+  out[2 * j + (0 ^ sw)] = lo;
+  out[2 * j + (1 ^ sw)] = hi;
+}
+
 int table_init_tc(Table *t) {
   t->tmap_valid = 0;
   t->packed = nullptr;
+  t->packed_h = nullptr;
   // 32 MB of the pre-swizzled table per column chunk: 4096 tiles of 8 KB at D = 8, fewer (larger) tiles beyond
   t->tc_chunk_tiles = 4096 / (t->dim >= 8 ? t->dim / 8 : 1);
   if (const char *e = getenv("PCV_TC_CHUNK_TILES")) {   // test hook: force chunking on small catalogs
@@ -769,18 +906,39 @@ int table_init_tc(Table *t) {
   }
   t->packed = p;
   t->tmap_valid = 1;
+  // f16 filter image (D = 8, row norms that f16 products can carry): built eagerly, so that the first select call may
+  // already be inside a CUDA graph capture
+  if (t->dim == 8 && t->max_row_norm > 0.f && t->max_row_norm < 1.0e4f) {
+    void *ph = nullptr;
+    e = cudaMalloc(&ph, (size_t)t->n_rows * 32);
+    if (e == cudaSuccess) {
+      pack_h16_kernel<<<(unsigned)((t->n_rows + 255) / 256), 256>>>(reinterpret_cast<const float4 *>(t->W), t->n_rows,
+                                                                    reinterpret_cast<uint4 *>(ph));
+      count_launch();
+      e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      if (ph) cudaFree(ph);
+      set_error("pcv_table_create: f16 table image -> %s", cudaGetErrorString(e));
+      return PCV_ERR_CUDA;
+    }
+    t->packed_h = ph;
+  }
   return PCV_OK;
 }
 
 void table_free_tc(Table *t) {
   if (t->packed) cudaFree(t->packed);
   t->packed = nullptr;
+  if (t->packed_h) cudaFree(t->packed_h);
+  t->packed_h = nullptr;
 }
 
 void launch_select_finalize(const float *pv, const int32_t *pi, int n_parts, int64_t M, int64_t row_offset,
                             int64_t *out_idx, float *out_val, cudaStream_t st);
 
-template <int KA>
+template <int KA, bool F16 = false>
 static int score_select_tc_impl(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val, void *ws,
                                 size_t ws_bytes, cudaStream_t st) {
   constexpr int D = 8 * KA;
@@ -798,11 +956,13 @@ static int score_select_tc_impl(const Table *t, const float *Q, int64_t M, int64
   const size_t smem = sizeof(TcSmem<KA>) + 1024;
   static bool attr_set[64] = {false};
   if (!attr_set[t->device & 63]) {
-    PCV_CUDA(cudaFuncSetAttribute(score_select_tc_kernel<KA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCV_CUDA((cudaFuncSetAttribute(score_select_tc_kernel<KA, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     attr_set[t->device & 63] = true;
   }
-  // |tf32 chain - fp32 chain| <= 1.25 * 2^-9 * |q| * max|w|; the band is twice that
-  const float band_scale = 2.0f * 1.25f * 0.001953125f * t->max_row_norm;
+  // |tf32 chain - fp32 chain| <= 1.25 * 2^-9 * |q| * max|w|; the band is twice that.  The f16 filter gets max|w| (+0.3 %)
+  // instead: it scales every query row into a fixed range, where its band is the constant TC_H_BAND
+  const float band_scale = F16 ? t->max_row_norm * 1.003f : 2.0f * 1.25f * 0.001953125f * t->max_row_norm;
+  const float *Wsw = F16 ? reinterpret_cast<const float *>(t->packed_h) : t->packed;
   for (int64_t r0 = 0; r0 < M; r0 += Mg) {   // row groups reuse the workspace back to back on the stream
     const int64_t m = (M - r0 < Mg) ? (M - r0) : Mg;
     const float *Qg = Q + r0 * D;
@@ -816,12 +976,12 @@ static int score_select_tc_impl(const Table *t, const float *Q, int64_t M, int64
     float *rr = reinterpret_cast<float *>(ovf_ent + g.ovf_cap);        // [n_sr]
     int32_t *cc = reinterpret_cast<int32_t *>(rr + n_sr);              // [n_sr]
     int32_t *ovf_row = cc + n_sr;                                      // [ovf_cap]
-    score_select_tc_kernel<KA><<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(t->packed, t->W, t->n_rows, Qg, m, g.T, g.Tc, g.row_tiles,
+    score_select_tc_kernel<KA, F16><<<(unsigned)g.grid, SEL_THREADS, smem, st>>>(Wsw, t->W, t->n_rows, Qg, m, g.T, g.Tc, g.row_tiles,
                                                                        g.slots, band_scale, rr, cc, ent, row_best, ovf_ent,
                                                                        ovf_row, g.ovf_cap / (unsigned)g.grid);
     PCV_LAUNCH_CHECK();
     tc_refine_kernel<D><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(t->W, t->n_rows, t->row_offset, Qg, m, g.T, g.Tc, g.row_tiles,
-                                                             g.slots, g.grid, band_scale, rr, cc, ent, row_best, ovf_count, out_idx + r0,
+                                                             g.slots, g.grid, band_scale, F16 ? TC_H_BAND : 0.f, rr, cc, ent, row_best, ovf_count, out_idx + r0,
                                                              out_val ? out_val + r0 : nullptr);
     if (cudaPeekAtLastError() != cudaSuccess) {
       // the filter ran but the kernel that re-zeroes the head did not launch: heal the workspace here, so that a
@@ -836,8 +996,17 @@ static int score_select_tc_impl(const Table *t, const float *Q, int64_t M, int64
   return PCV_OK;
 }
 
+bool score_select_tc_f16_supported(const Table *t) { return t->dim == 8 && t->tmap_valid && t->packed_h != nullptr; }
+
 int score_select_tc(const Table *t, const float *Q, int64_t M, int64_t *out_idx, float *out_val, void *ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, cudaStream_t st, int f16) {
+  if (f16) {
+    if (!score_select_tc_f16_supported(t)) {
+      set_error("score_select(tcgen05 f16): needs dim 8 and a table whose row norms fit f16 (dim %d, max|w| %g)", t->dim, (double)t->max_row_norm);
+      return PCV_ERR_UNSUPPORTED;
+    }
+    return score_select_tc_impl<1, true>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
+  }
   switch (t->dim) {
     case 8: return score_select_tc_impl<1>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);
     case 16: return score_select_tc_impl<2>(t, Q, M, out_idx, out_val, ws, ws_bytes, st);

@@ -184,7 +184,8 @@ def score_select(table, Q, mode="greedy", noise=None, seed=0, offset=0, engine="
         raise L.PcvError("Q has dim %d, table has dim %d" % (D, table.dim))
     opts = L.SelectOpts()
     opts.mode = L.SELECT_GREEDY if mode == "greedy" else L.SELECT_EXPRACE
-    opts.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05}[engine]
+    opts.engine = {"auto": L.ENGINE_AUTO, "simt": L.ENGINE_SIMT, "tcgen05": L.ENGINE_TCGEN05,
+                   "tcgen05_f16": L.ENGINE_TCGEN05_F16}[engine]
     if noise is not None:
         noise = _f32(noise, "noise")
         if tuple(noise.shape) != (M, table.n_rows):

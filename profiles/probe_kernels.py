@@ -50,6 +50,15 @@ def p_select():      # score_select_tc_kernel + tc_refine_kernel at C4
     timed("select_c4 (1M x 20480)", lambda: ops.score_select(tab, Q, "greedy"), 1e6 * 20480 / 1e3, "T logits/s")
 
 
+def p_select_f16():  # the f16 filter (packed TMEM reads, VIMNMX3.U16x2) at C4 and at the pivot-pick shape
+    W = table(1000000)
+    tab = ops.Table(W)
+    for M in (20480, 4096):
+        Q = torch.randn(M, 8, generator=G, device=DEV) * 0.5
+        timed("select_c4 tf32 (1M x %d)" % M, lambda: ops.score_select(tab, Q, "greedy", engine="tcgen05"), 1e6 * M / 1e3, "T logits/s")
+        timed("select_c4 f16  (1M x %d)" % M, lambda: ops.score_select(tab, Q, "greedy", engine="tcgen05_f16"), 1e6 * M / 1e3, "T logits/s")
+
+
 def p_select_d128():   # the same filter at D = 128 (16 accumulating MMAs per tile): tensor-pipe evidence
     W, Q = table(1000000, 128), torch.randn(20480, 128, generator=G, device=DEV) * 0.5
     tab = ops.Table(W)

@@ -17,6 +17,13 @@ def ops():
     return o
 
 
+@pytest.fixture(params=["tcgen05", "tcgen05_f16"])
+def tc_engine(request):
+    """D = 8 runs on both tensor-core filters: tf32 operands / fp32 accumulators, and f16 operands / f16 accumulators
+    (packed TMEM reads, 16-bit packed maxima); the exact refine makes their results identical."""
+    return request.param
+
+
 def _unit(rng, n, d=8):
     W = rng.standard_normal((n, d)).astype(np.float32)
     return W / np.linalg.norm(W, axis=1, keepdims=True)
@@ -24,7 +31,7 @@ def _unit(rng, n, d=8):
 
 @pytest.mark.parametrize("n_items,M", [(256, 128), (300, 1), (2048, 128), (2049, 130), (4095, 77), (50000, 1024),
                                        (65536, 300), (100003, 515), (3707, 320)])
-def test_tc_matches_oracle(ops, n_items, M):
+def test_tc_matches_oracle(ops, n_items, M, tc_engine):
     rng = np.random.default_rng(n_items * 7 + M)
     W = _unit(rng, n_items)
     Q = (rng.standard_normal((M, 8)) * rng.uniform(0.05, 3.0, (M, 1))).astype(np.float32)
@@ -34,7 +41,7 @@ def test_tc_matches_oracle(ops, n_items, M):
         W[300] = W[5]
         Q[0] = 1.7 * W[5]
     tab = ops.Table(T(W))
-    idx, val = ops.score_select(tab, T(Q), "greedy", engine="tcgen05")
+    idx, val = ops.score_select(tab, T(Q), "greedy", engine=tc_engine)
     oi, ov = oracle.score_select(W, Q)
     assert np.array_equal(N(idx), oi)
     assert np.array_equal(N(val), ov)       # the refine is the exact fp32 FMA chain: bitwise
@@ -44,10 +51,10 @@ def test_tc_matches_oracle(ops, n_items, M):
     assert torch.equal(idx, si) and torch.equal(val, sv)
 
 
-def test_tc_golden_dims8(ops, golden):
+def test_tc_golden_dims8(ops, golden, tc_engine):
     fx = golden("dims")
     tab = ops.Table(T(fx["d8/W"]))
-    idx, val = ops.score_select(tab, T(fx["d8/Q"]), "greedy", engine="tcgen05")
+    idx, val = ops.score_select(tab, T(fx["d8/Q"]), "greedy", engine=tc_engine)
     assert np.array_equal(N(idx), fx["d8/idx"]) and np.array_equal(N(val), fx["d8/val"])   # == torch.mm + torch.max
 
 
@@ -87,23 +94,23 @@ def test_tc_other_dims_match_oracle(ops, n_items, M, D):
     assert torch.equal(idx, ai) and torch.equal(val, av)
 
 
-def test_tc_all_equal_and_heavy_ties(ops):
+def test_tc_all_equal_and_heavy_ties(ops, tc_engine):
     """Every item inside the band: lists collapse continuously; the first index must still win."""
     W = np.tile(np.array([[0.5, 0.5, 0.5, 0.5, 0, 0, 0, 0]], dtype=np.float32), (5000, 1))
     Q = np.ones((130, 8), dtype=np.float32)
-    idx, _ = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine="tcgen05")
+    idx, _ = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine=tc_engine)
     assert np.array_equal(N(idx), np.zeros(130, dtype=np.int64))
     rng = np.random.default_rng(0)
     W2 = _unit(rng, 6000)
     W2[1000:1400] = W2[999]          # 401 exact duplicates of the best row for Q2[0]
     Q2 = rng.standard_normal((64, 8)).astype(np.float32)
     Q2[0] = W2[999]
-    idx2, val2 = ops.score_select(ops.Table(T(W2)), T(Q2), "greedy", engine="tcgen05")
+    idx2, val2 = ops.score_select(ops.Table(T(W2)), T(Q2), "greedy", engine=tc_engine)
     oi, ov = oracle.score_select(W2, Q2)
     assert np.array_equal(N(idx2), oi) and np.array_equal(N(val2), ov) and N(idx2)[0] == 999
 
 
-def test_tc_near_ties_inside_tf32_error(ops):
+def test_tc_near_ties_inside_tf32_error(ops, tc_engine):
     """Items whose exact scores differ by less than the tf32 error: the filter may misorder them,
     the refine must not."""
     rng = np.random.default_rng(42)
@@ -115,22 +122,22 @@ def test_tc_near_ties_inside_tf32_error(ops):
         pert = base + d * rng.standard_normal(8)
         W[j] = (pert / np.linalg.norm(pert)).astype(np.float32)
     Q = np.repeat(q[None], 128, 0).astype(np.float32) * np.linspace(0.1, 4, 128, dtype=np.float32)[:, None]
-    idx, val = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine="tcgen05")
+    idx, val = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine=tc_engine)
     oi, ov = oracle.score_select(W, Q)
     assert np.array_equal(N(idx), oi) and np.array_equal(N(val), ov)
 
 
-def test_tc_unnormalised_table_and_zero_query(ops):
+def test_tc_unnormalised_table_and_zero_query(ops, tc_engine):
     rng = np.random.default_rng(9)
     W = (rng.standard_normal((7000, 8)) * rng.uniform(0.1, 20, (7000, 1))).astype(np.float32)
     Q = rng.standard_normal((200, 8)).astype(np.float32) * 5
     Q[3] = 0       # all scores equal (0): index 0 wins
-    idx, val = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine="tcgen05")
+    idx, val = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine=tc_engine)
     oi, ov = oracle.score_select(W, Q)
     assert np.array_equal(N(idx), oi) and np.array_equal(N(val), ov) and N(idx)[3] == 0
 
 
-def test_tc_full_size_properties(ops):
+def test_tc_full_size_properties(ops, tc_engine):
     """BASELINE C4 size (1M items, 20480 rows): shard-merge invariance, planted maxima, and the
     winning value re-derived from the returned index (no oracle run at this size)."""
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -140,7 +147,7 @@ def test_tc_full_size_properties(ops):
     plant = torch.randint(0, n_items, (64,), generator=g, device="cuda")
     Q[:64] = 2.5 * W[plant]                      # the planted row is the unique maximiser (cos = 1)
     full = ops.Table(W)
-    idx, val = ops.score_select(full, Q, "greedy", engine="tcgen05")
+    idx, val = ops.score_select(full, Q, "greedy", engine=tc_engine)
     assert torch.equal(W[idx[:64]], W[plant])
     # value == exact chain of the returned index, and no random probe beats it
     probe = torch.randint(0, n_items, (M, 64), generator=g, device="cuda")
@@ -151,7 +158,7 @@ def test_tc_full_size_properties(ops):
     vals, idxs = [], []
     for s in range(G):
         t = ops.Table(W[s * per:(s + 1) * per], row_offset=s * per)
-        i, v = ops.score_select(t, Q, "greedy", engine="tcgen05")
+        i, v = ops.score_select(t, Q, "greedy", engine=tc_engine)
         vals.append(v)
         idxs.append(i)
     mi, mv = ops.vp_merge_select(torch.stack(vals), torch.stack(idxs))
@@ -160,7 +167,7 @@ def test_tc_full_size_properties(ops):
     assert torch.equal(si, idx[:2048]) and torch.equal(sv, val[:2048])
 
 
-def test_tc_row_groups_and_max_size(ops):
+def test_tc_row_groups_and_max_size(ops, tc_engine):
     """M large enough that the workspace budget forces several row groups (C5-style: 10 M items)."""
     g = torch.Generator(device="cuda").manual_seed(5)
     n_items, M = 10_000_000, 16384
@@ -170,7 +177,7 @@ def test_tc_row_groups_and_max_size(ops):
     Q[::7] = 1.5 * W[plant[::7]]
     tab = ops.Table(W)
     assert tab.workspace("select", M).numel() <= (200 << 20)
-    idx, val = ops.score_select(tab, Q, "greedy", engine="tcgen05")
+    idx, val = ops.score_select(tab, Q, "greedy", engine=tc_engine)
     assert torch.equal(W[idx[::7]], W[plant[::7]])
     exact = (W[idx] * Q).sum(-1)
     assert bool(((exact - val).abs() <= 1e-5).all())
@@ -179,7 +186,7 @@ def test_tc_row_groups_and_max_size(ops):
 
 
 @pytest.mark.parametrize("n_items,M,chunk_tiles", [(50000, 700, 16), (100003, 515, 64), (9000, 300, 3), (65536, 1500, 100)])
-def test_tc_column_chunks(ops, monkeypatch, n_items, M, chunk_tiles):
+def test_tc_column_chunks(ops, monkeypatch, n_items, M, chunk_tiles, tc_engine):
     """Catalogs beyond the L2 are walked in column chunks (32 MB each in production); PCV_TC_CHUNK_TILES forces the
     chunked partition on small catalogs: same bits as the oracle, ties across chunks -> lowest index, heavy ties
     (flagged streams, overflow lists) inside a chunk."""
@@ -194,10 +201,10 @@ def test_tc_column_chunks(ops, monkeypatch, n_items, M, chunk_tiles):
     W[n_items // 3: n_items // 3 + 700] = W[n_items // 3]      # 700-way tie block inside one chunk
     Q[1] = 2.0 * W[n_items // 3]
     tab = ops.Table(T(W))
-    idx, val = ops.score_select(tab, T(Q), "greedy", engine="tcgen05")
+    idx, val = ops.score_select(tab, T(Q), "greedy", engine=tc_engine)
     oi, ov = oracle.score_select(W, Q)
     assert np.array_equal(N(idx), oi) and np.array_equal(N(val), ov)
     assert N(idx)[0] == 5 and N(idx)[1] == n_items // 3
     monkeypatch.delenv("PCV_TC_CHUNK_TILES")
-    idx1, val1 = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine="tcgen05")     # one chunk: same answer
+    idx1, val1 = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine=tc_engine)     # one chunk: same answer
     assert torch.equal(idx, idx1) and torch.equal(val, val1)
