@@ -506,20 +506,26 @@ def measure_generate(D, args, wname, mode, window_s, vp=False, full=True, cpu_se
         peak_tf = pk.get("bf16_tflops", 1590.0)
         flops = 2.0 * Dm * N * (B * L_)
         ach = flops / (dom_ms * 1e-3) / 1e12
-        tc = args.engine in ("auto", "tcgen05") and N >= 2048
-        kname = ("score_select_tc_kernel (tcgen05 kind::tf32 filter) + tc_refine_kernel (exact fp32)" if tc
-                 else "score_select_kernel<D=%d> (exact fp32 SIMT) + finalize" % Dm)
+        tc = args.engine in ("auto", "tcgen05", "tcgen05_f16") and N >= 2048
+        f16 = tc and Dm == 8 and args.engine != "tcgen05"
+        kname = (("score_select_tc_kernel (tcgen05 kind::%s filter) + tc_refine_kernel (exact fp32)" % ("f16, f16 accumulators" if f16 else "tf32"))
+                 if tc else "score_select_kernel<D=%d> (exact fp32 SIMT) + finalize" % Dm)
         out["roofline"] = {
             "bound": "tensor", "kernel": "%s, M=%d rows x N=%d items, D=%d" % (kname, B * L_, N, Dm),
             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS bf16; the kernel is kind::tf32 whose nominal peak is half of bf16's)"
+            "peak_source": (("MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS bf16; %s)" % (
+                                "the kernel is kind::f16 with K = 16, of which D = 8 are real dimensions" if f16 else
+                                "the kernel is kind::tf32 whose nominal peak is half of bf16's"))
                             if pk else "fallback 1590 (B200_PROFILING.md)"),
             "traffic": traffic_of(wname, B * L_, N) if not vp else None,
             "algorithmic_bytes": N * Dm * 4 + B * L_ * (Dm * 4 + 8), "ms_avg_launch": dom_ms,
             "logits_per_s": (B * L_) * N / (dom_ms * 1e-3),
-            "epilogue_roofline": {"note": "at D=8 the consumer of the logits bounds the kernel (SURVEY H2): TMEM read 64 B/clk/SMSP = "
-                                          "64 fp32 logits/clk/SM", "peak_logits_per_s": 64 * 148 * 1.965e9,
-                                  "frac": (B * L_) * N / (dom_ms * 1e-3) / (64 * 148 * 1.965e9)},
+            # at D = 8 the consumer of the logits bounds the kernel.  Measured (profiles/micro/tmem_f16.cu): a
+            # 128 x 256 tile is read from TMEM in 277 cycles as fp32 and in 142 cycles as packed f16; the MMA that makes it takes 128
+            "epilogue_roofline": {"note": "TMEM read of the accumulators, measured: 128x256 logits per %d cycles per SM (%s); the MMA "
+                                          "producing them takes 128" % ((142, "f16, .pack::16b") if f16 else (277, "fp32")),
+                                  "peak_logits_per_s": 32768 / (142.0 if f16 else 277.0) * 148 * 1.965e9,
+                                  "frac": (B * L_) * N / (dom_ms * 1e-3) / (32768 / (142.0 if f16 else 277.0) * 148 * 1.965e9)},
             "share_of_step": dom_ms / (ms / K),
             "timing": "CUDA events around a graph replay of the call alone on the decoder's queries, L2 flushed, %d replays after "
                       "the timed region (eager launch of the same call: %s ms)" % (KP, "%.4f" % eager_ms if eager_ms else "n/a"),
@@ -820,7 +826,8 @@ def main():
     ap.add_argument("--n-neg", type=int, default=0, help="train mode: negatives per row (0 = the whole catalog)")
     ap.add_argument("--ce-engine", default="tf32", choices=["exact", "tf32"],
                     help="train mode, full catalog: CE logits in exact fp32 (SIMT) or tf32 on the tensor cores (C3 is a reduced-precision config)")
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_f16"],
+                    help="score+select engine: auto = tensor cores (dim 8: the f16 filter, else tf32) with the exact fp32 refine")
     ap.add_argument("--mlp-engine", default="auto", choices=["exact", "tc", "auto"],
                     help="fused MLP blocks at inference: tc = tcgen05 3xTF32 (fp32-grade), exact = FFMA chain bit-identical to the oracle, "
                          "auto = tc for batches of >= 2048 rows")

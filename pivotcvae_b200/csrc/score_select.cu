@@ -427,9 +427,9 @@ int pcv_score_select(const pcv_table *th, const float *Q, int64_t M,
   cudaStream_t st = (cudaStream_t)stream;
 
   int engine = opts->engine;
-  if (engine == PCV_ENGINE_AUTO)  // tensor cores whenever the shape allows and the catalog is not tiny
+  if (engine == PCV_ENGINE_AUTO)  // tensor cores whenever the shape allows and the catalog is not tiny; dim 8: the f16 filter
     engine = (opts->mode == PCV_SELECT_GREEDY && score_select_tc_supported(t) && t->n_rows >= 2048)
-                 ? PCV_ENGINE_TCGEN05 : PCV_ENGINE_SIMT;
+                 ? (score_select_tc_f16_supported(t) ? PCV_ENGINE_TCGEN05_F16 : PCV_ENGINE_TCGEN05) : PCV_ENGINE_SIMT;
   if (engine == PCV_ENGINE_TCGEN05 || engine == PCV_ENGINE_TCGEN05_F16) {
     if (opts->mode != PCV_SELECT_GREEDY || !score_select_tc_supported(t)) {
       set_error("score_select: tcgen05 engine needs greedy mode and dim 8, 16, 32, 64 or 128 (dim %d, mode %d)", t->dim, opts->mode);
