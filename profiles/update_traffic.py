@@ -23,7 +23,7 @@ def val(row, name):
     return float(row[i].replace(",", "")) * scale.get(units[i], 1.0)
 
 
-filt = [r for r in rows[2:] if "score_select_tc_kernel<1>" in r[hdr.index("Kernel Name")] or
+filt = [r for r in rows[2:] if "score_select_tc_kernel<1" in r[hdr.index("Kernel Name")] or
         ("score_select_tc_kernel(" in r[hdr.index("Kernel Name")])]
 # probe order: select (C4: 1 M x 20480), then select_d128 (another instantiation), then select_c2 (50 k x 10240), ...
 out = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (score_select_tc_kernel<1>), one launch, "
