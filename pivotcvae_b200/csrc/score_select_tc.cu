@@ -533,6 +533,7 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (threadIdx.x == 64 && gt >= 40 && gt < 44) TC_TRACE(5 + 2 * (gt - 40));
         const uint32_t taddr = taddr0 + buf * TC_BN;
+        bool released = false;     // the TMEM buffer goes back as soon as this warp's columns are in registers
         uint32_t va[32], vb[32];
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
         // (f16 filter: ONE packed load brings the slice's 64 columns)
@@ -552,6 +553,12 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
         if constexpr (F16) {
           static_assert(SEL_SW == 64, "one packed load per slice");
           (void)vb;
+          // the slice's 64 values are in registers: hand the TMEM buffer back BEFORE reducing them, so that the MMA of
+          // the tile after next starts one reduction earlier (the buffer round trip, not a pipe, bounds the kernel)
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
+          released = true;
           if (t >= n_full) {   // last tile of the table: columns beyond its end (stale ring data) -> 0, below every live score
             const int n_valid = (int)min((int64_t)SEL_SW, j_end - (int64_t)jb0);  // may be <= 0
 #pragma unroll
@@ -568,7 +575,15 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
             TC_LD32(vb, taddr + (c + 1) * 32);
             process(va, jb0 + c * 32);
             TC_WAIT_LD(vb);
-            if (c + 2 < NCH) TC_LD32(va, taddr + (c + 2) * 32);
+            if (c + 2 < NCH) {
+              TC_LD32(va, taddr + (c + 2) * 32);
+            } else {
+              // the slice's last values are in registers: hand the TMEM buffer back before reducing them
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
+              released = true;
+            }
             process(vb, jb0 + (c + 1) * 32);
             if (c + 2 < NCH) TC_WAIT_LD(va);
           }
@@ -581,9 +596,11 @@ score_select_tc_kernel(const float *__restrict__ Wsw, const float *__restrict__ 
             process(va, jb0 + c * 32);
           }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
+        if (!released) {   // (tail tile of the tf32 filter)
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_u32(tempty_u32 + buf * 8);
+        }
         if (threadIdx.x == 64 && gt >= 40 && gt < 44) TC_TRACE(6 + 2 * (gt - 40));
       }
       if (live) {
