@@ -129,10 +129,11 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float (&g)[1
 // (profiles/micro/tmem_f16.cu: 142 vs 277 cycles per 128 x 256 tile), and VIMNMX3.U16x2 takes the maximum of SIX
 // 16-bit values per instruction — IF the approximate scores are non-negative, so that their f16 bit patterns order
 // like unsigned integers.  kind::f16 has K = 16 and D = 8 uses half of it: dimension 8 carries a constant,
-// q'_8 = w_8 = 1, and the query row is scaled by a power of two so that |q'| max|w| is in [0.5, 0.997]:
+// q'_8 = w_8 = 1, and the query row is scaled so that |q'| max|w| = 0.987:
 //     a~ = sum_k f16(q'_k) f16(w_k) + 1   in (0, 2),   |a~ - (s' + 1)| <= 2^-10 (operands, RN) + 2^-10 (result) = 2^-9.
 // Scaling a row by 2^-e does not move its arg-max, so the filter runs entirely in that scaled, shifted domain with the
 // CONSTANT band 2 * 1.25 * 2^-9; the refine re-scores the surviving chunks with the exact fp32 chain as before.
+// (The scale is 0.99 / (|q| max|w| 1.003), not a power of two: see tc_h_scale.)
 constexpr float TC_H_BAND = 2.0f * 1.25f * 0.001953125f;
 constexpr uint32_t TC_IDESC_F16 = (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -165,14 +166,16 @@ __device__ __forceinline__ void chunk_max_u16x2(const uint32_t *v, uint32_t &b0,
   b0 = __vimax3_u16x2(a0, a1, a2);
   b1 = __vimax3_u16x2(a3, a4, v[15]);
 }
-// power-of-two scale of a query row of the f16 filter: |q| wmax 2^-e in [0.5, 1) with wmax inflated by 0.3 %
+// scale of a query row of the f16 filter: |q'| max|w| = 0.99 / 1.003 (wmax_s is max|w| inflated by 0.3 %).  The scale
+// need not be a power of two: q' = fl(c q) adds 2^-24 relative to an error budget of 2^-10, and a positive scale does
+// not move the row's arg-max.  Keeping the product at the TOP of [0.5, 1) matters: the band is a constant of the scaled
+// domain, so relative to |q| it is 1 / (|q'| max|w|) times wider — at 0.5 twice the tf32 filter's, and with it the
+// number of chunks a stream hands over (measured at 10 M items: streams overflowing their four hand-over slots and
+// being re-scanned exactly made the refine 200x slower).
 __device__ __forceinline__ float tc_h_scale(float ss, float wmax_s) {
   const float t = sqrtf(ss) * wmax_s;
-  if (!(t > 0.f) || !(t < 3.0e38f)) return 1.f;      // zero / non-finite row: every approximate score is the constant
-  int e;
-  frexpf(t, &e);
-  e = max(-100, min(100, e));
-  return ldexpf(1.f, -e);
+  if (!(t > 1.0e-30f) || !(t < 1.0e30f)) return 1.f;      // zero / non-finite row: every approximate score is the constant
+  return 0.99f / t;
 }
 
 // Packed exact winner of a row among its overflow chunks, merged with a 64-bit atomicMax:

@@ -33,7 +33,7 @@ for shp in [a for a in sys.argv[1:] if "x" in a] or ["2048x128"]:
     Q = torch.randn(m, 8, generator=g, device="cuda") * 0.5
     tab = ops.Table(W)
     for _ in range(3):
-        ops.score_select(tab, Q, "greedy", engine="tcgen05")
+        ops.score_select(tab, Q, "greedy", engine=os.environ.get("TRACE_ENGINE", "tcgen05"))
     torch.cuda.synchronize()
     t = (ctypes.c_longlong * 16)()
     _lib.load().pcv_debug_tc_trace(t)
