@@ -208,3 +208,36 @@ def test_tc_column_chunks(ops, monkeypatch, n_items, M, chunk_tiles, tc_engine):
     monkeypatch.delenv("PCV_TC_CHUNK_TILES")
     idx1, val1 = ops.score_select(ops.Table(T(W)), T(Q), "greedy", engine=tc_engine)     # one chunk: same answer
     assert torch.equal(idx, idx1) and torch.equal(val, val1)
+
+
+def test_f16_filter_hands_over_no_more_than_the_tf32_filter(ops):
+    """Regression guard for the f16 filter's band.  Its band is a constant of the scaled domain, so relative to |q| it
+    is 1 / (|q'| max|w|) times wider: with a power-of-two scale (|q'| max|w| anywhere in [0.5, 1)) streams at 10 M
+    items overflowed their four hand-over slots, were flagged and re-scanned exactly by the refine kernel — still
+    bit-exact, but the call took 1.4x (16384 rows) to 2.6x (65536 rows) the tf32 filter's time instead of 0.84x.
+    Same results, and the f16 call must not be slower than the tf32 one by more than a generous margin."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n_items, M = 10_000_000, 16384
+    W = torch.nn.functional.normalize(torch.randn(n_items, 8, generator=g, device="cuda"), dim=1)
+    Q = torch.randn(M, 8, generator=g, device="cuda") * torch.empty(M, 1, device="cuda").uniform_(0.3, 3.0, generator=g)
+    tab = ops.Table(W)
+
+    def run(engine):
+        out = ops.score_select(tab, Q, "greedy", engine=engine)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.score_select(tab, Q, "greedy", engine=engine)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return out, sorted(ts)[2]
+
+    (ti, tv), t_tf32 = run("tcgen05")
+    (hi, hv), t_f16 = run("tcgen05_f16")
+    assert torch.equal(ti, hi) and torch.equal(tv, hv)
+    print("10 M x %d: tf32 filter %.2f ms, f16 filter %.2f ms" % (M, t_tf32, t_f16))
+    assert t_f16 < 1.25 * t_tf32
+
