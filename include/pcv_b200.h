@@ -59,7 +59,10 @@ typedef struct pcv_table pcv_table;
 /* W: [n_rows, dim] fp32 row-major, 16-byte aligned.  row_offset is the global
  * index of row 0 (vocab-parallel shards); indices returned by
  * pcv_score_select are global (= local + row_offset).  The table is borrowed,
- * not copied: it must outlive the handle.  dim must be a multiple of 4, <= 128. */
+ * not copied: it must outlive the handle.  dim must be a multiple of 4, <= 128.
+ * The handle owns the packed images the tensor-core engines stream with TMA: dim 8/16/32/64/128 the pre-swizzled fp32
+ * copy (dim * 4 bytes per row), dim 8 with row norms in (0, 1e4) also the f16 image of the f16 filter (32 bytes per
+ * row); they are snapshots: re-create the handle after the table changes. */
 int pcv_table_create(const float *W, int64_t n_rows, int dim, int64_t row_offset,
                      pcv_table **out);
 void pcv_table_destroy(pcv_table *t);
