@@ -259,3 +259,44 @@ def test_mlp_engine_policy_is_validated_and_scoped():
     with pytest.raises(ValueError):
         ops.mlp_engine("bf16")
     assert ops.TC_MAX_IN == 64 and ops.TC_MAX_WIDTH == 256 and ops.TC_MIN_ROWS >= 1024
+
+
+def test_f16_filter_error_bound_in_numpy():
+    """The band of the f16 select filter (csrc/score_select_tc.cu) rests on |a~ - (s' + 1)| <= 2^-9 for
+    a~ = f16(sum_k f16(q'_k) f16(w_k) + 1), q' = q * 0.99 / (|q| max|w| 1.003): operands rounded to nearest (2^-11 each),
+    products and the 9-term sum exact in the tensor core, ONE final conversion of a value in (0, 2) to f16 (truncation
+    assumed: the worse case).  Emulated here in float64 / float16 over random and adversarial rows; also: the shifted
+    scores are strictly positive and below 2, so their f16 bit patterns order like unsigned integers."""
+    rng = np.random.default_rng(0)
+
+    def trunc_f16(x):      # round toward zero to float16 (positive inputs)
+        h = x.astype(np.float16)
+        too_big = h.astype(np.float64) > x
+        return np.where(too_big, np.nextafter(h, np.float16(0)), h).astype(np.float16)
+
+    worst = 0.0
+    for trial in range(40):
+        n = 4000
+        W = rng.standard_normal((n, 8)) * rng.uniform(0.01, 30.0)
+        if trial % 3 == 0:
+            W /= np.linalg.norm(W, axis=1, keepdims=True)
+        W = W.astype(np.float32)
+        q = (rng.standard_normal(8) * 10.0 ** rng.uniform(-6, 6)).astype(np.float32)
+        if trial % 5 == 0:
+            q = (W[rng.integers(n)] * rng.uniform(0.1, 50)).astype(np.float32)       # parallel to an item: score at the ceiling
+        if trial % 7 == 0:
+            q = (-W[rng.integers(n)] * rng.uniform(0.1, 50)).astype(np.float32)      # anti-parallel: shifted score near 0
+        wmax = float(np.linalg.norm(W.astype(np.float64), axis=1).max()) * 1.000001 * 1.003
+        c = np.float32(0.99) / np.float32(np.sqrt(np.float32((q.astype(np.float64) ** 2).sum())) * np.float32(wmax))
+        qs = (q * c).astype(np.float32)
+        exact = W.astype(np.float64) @ qs.astype(np.float64) + 1.0                  # s' + 1
+        approx = W.astype(np.float16).astype(np.float64) @ qs.astype(np.float16).astype(np.float64) + 1.0
+        assert approx.min() > 0.0 and approx.max() < 2.0
+        a16 = trunc_f16(approx)
+        assert (a16.view(np.uint16) > 0).all() and (a16.astype(np.float64) < 2.0).all()
+        worst = max(worst, float(np.abs(a16.astype(np.float64) - exact).max()))
+        # unsigned order of the bit patterns == order of the values
+        order = np.argsort(a16.astype(np.float64), kind="stable")
+        assert (np.diff(a16.view(np.uint16)[order].astype(np.int64)) >= 0).all()
+    assert worst <= 2.0 ** -9, worst
+    assert 2.0 * 1.25 * 2.0 ** -9 >= 2.0 * worst        # the band the kernel uses (TC_H_BAND)
